@@ -1,0 +1,192 @@
+// extern "C" surface of libfenerf_b200 (include/fenerf_b200.h): argument validation, precision
+// dispatch and the five-launch render pipeline.  No torch types, no allocation, no global state
+// beyond the thread-local error string and the launch counter.
+#include "common.cuh"
+
+namespace fn {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+}  // namespace fn
+
+using namespace fn;
+
+namespace {
+
+struct Workspace {
+    size_t points_c, z_c, dirs, origins, raw_c, z_f, points_f, raw_f, guard, total;
+};
+
+Workspace plan_workspace(const fenerf_render_desc* rd, int C) {
+    Workspace w;
+    size_t n_rays = (size_t)rd->batch * rd->img_h * rd->img_w;
+    size_t pc = n_rays * rd->num_steps;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = fn_align_up(off + bytes, 256); return o; };
+    w.points_c = take(pc * 3 * 4);
+    w.z_c = take(pc * 4);
+    w.dirs = take(n_rays * 3 * 4);
+    w.origins = take((size_t)rd->batch * 3 * 4);
+    w.raw_c = take(pc * C * 4);
+    w.z_f = take(rd->hierarchical ? pc * 4 : 4);
+    w.points_f = take(rd->hierarchical ? pc * 3 * 4 : 4);
+    w.raw_f = take(rd->hierarchical ? pc * C * 4 : 4);
+    w.guard = take((n_rays + 1) * 4);
+    w.total = off;
+    return w;
+}
+
+int check_render_desc(const fenerf_render_desc* rd) {
+    FN_REQUIRE(rd, "render desc is NULL");
+    FN_REQUIRE(rd->batch >= 1 && rd->img_h >= 1 && rd->img_w >= 1, "bad batch/img size %d %dx%d", rd->batch, rd->img_h,
+               rd->img_w);
+    FN_REQUIRE(rd->num_steps >= 2 && rd->num_steps <= 64, "num_steps %d outside [2, 64]", rd->num_steps);
+    if (rd->clamp_mode != FENERF_CLAMP_RELU && rd->clamp_mode != FENERF_CLAMP_SOFTPLUS)
+        return fail(FENERF_E_CLAMP_MODE, "Need to choose clamp mode");
+    FN_REQUIRE(rd->fill_mode >= FENERF_FILL_NONE && rd->fill_mode <= FENERF_FILL_EVAL_WHITE_BACK, "unknown fill_mode %d",
+               rd->fill_mode);
+    FN_REQUIRE(rd->precision >= FENERF_PRECISION_EXACT && rd->precision <= FENERF_PRECISION_GUARD, "unknown precision %d",
+               rd->precision);
+    return 0;
+}
+
+int run_field(const FnLayout& L, const void* packed, const float* points, const float* dirs, const float* film,
+              int batch, long long ppb, int dir_group, int lock_dirs, int precision, float* out, cudaStream_t st) {
+    const unsigned char* pk = static_cast<const unsigned char*>(packed);
+    if (precision == FENERF_PRECISION_EXACT)
+        return siren_points_exact(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, nullptr, 0, out, st);
+    return siren_points_fast(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, st);
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* fenerf_last_error(void) { return g_err; }
+int32_t fenerf_abi_version(void) { return FENERF_ABI_VERSION; }
+int64_t fenerf_launch_count(void) { return (int64_t)g_launches.load(); }
+
+size_t fenerf_packed_bytes(const fenerf_field_desc* field) {
+    FnLayout L;
+    if (fn_make_layout(field, &L) != 0) {
+        fail(FENERF_E_ARG, "unsupported field description");
+        return 0;
+    }
+    return L.total;
+}
+
+int fenerf_pack_field(const fenerf_field_desc* field, const fenerf_field_params* params, void* packed,
+                      size_t packed_bytes, void* stream) {
+    FnLayout L;
+    FN_REQUIRE(fn_make_layout(field, &L) == 0, "unsupported field description");
+    FN_REQUIRE(params && packed, "params/packed is NULL");
+    FN_REQUIRE(((uintptr_t)packed & 1023) == 0, "packed buffer must be 1024-byte aligned");
+    if (packed_bytes < L.total) return fail(FENERF_E_WORKSPACE, "packed buffer too small: %zu < %zu", packed_bytes, L.total);
+    return pack_field(field, L, params, packed, (cudaStream_t)stream);
+}
+
+int fenerf_siren_points(const fenerf_field_desc* field, const void* packed, const float* points, const float* dirs,
+                        const float* film, int32_t batch, int64_t points_per_batch, int32_t dir_group,
+                        int32_t precision, const int32_t* only_idx, int32_t n_only, float* out, void* stream) {
+    FnLayout L;
+    FN_REQUIRE(fn_make_layout(field, &L) == 0, "unsupported field description");
+    FN_REQUIRE(packed && points && film && out, "NULL argument");
+    FN_REQUIRE(dirs, "dirs is NULL (pass any (B,P/dir_group,3) tensor; the colour branch consumes it)");
+    FN_REQUIRE(batch >= 1 && points_per_batch >= 1 && dir_group >= 1, "bad sizes");
+    FN_REQUIRE(points_per_batch % dir_group == 0, "points_per_batch must be a multiple of dir_group");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (only_idx) {
+        if (n_only <= 0) return 0;
+        return siren_points_exact(L, (const unsigned char*)packed, points, dirs, film, batch, points_per_batch, dir_group,
+                                  0, only_idx, n_only, out, st);
+    }
+    FN_REQUIRE(precision >= FENERF_PRECISION_EXACT && precision <= FENERF_PRECISION_GUARD, "unknown precision %d", precision);
+    return run_field(L, packed, points, dirs, film, batch, points_per_batch, dir_group, 0, precision, out, st);
+}
+
+int fenerf_ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_lin, const float* z_lin,
+                     const float* cam2world, const float* rng_perturb, float* points, float* z_vals, float* dirs,
+                     float* origins, void* stream) {
+    if (int e = check_render_desc(rd)) return e;
+    FN_REQUIRE(x_lin && y_lin && z_lin && cam2world && rng_perturb && points && z_vals && dirs && origins, "NULL argument");
+    return ray_setup(rd, x_lin, y_lin, z_lin, cam2world, rng_perturb, points, z_vals, dirs, origins, (cudaStream_t)stream);
+}
+
+int fenerf_resample(const fenerf_render_desc* rd, int32_t out_dim, const float* raw_coarse, const float* z_vals,
+                    const float* dirs, const float* origins, const float* rng_noise, const float* rng_u, float* z_fine,
+                    float* points_fine, int64_t* inds, void* stream) {
+    if (int e = check_render_desc(rd)) return e;
+    FN_REQUIRE(raw_coarse && z_vals && dirs && origins && rng_u && z_fine && points_fine, "NULL argument");
+    FN_REQUIRE(out_dim >= 2 && out_dim <= 36, "out_dim %d unsupported", out_dim);
+    FN_REQUIRE(rd->noise_std == 0.f || rng_noise, "noise_std != 0 needs rng_noise");
+    return resample(rd, out_dim, raw_coarse, z_vals, dirs, origins, rd->noise_std != 0.f ? rng_noise : nullptr, rng_u,
+                    z_fine, points_fine, (long long*)inds, (cudaStream_t)stream);
+}
+
+int fenerf_composite(const fenerf_render_desc* rd, int32_t out_dim, const float* raw_coarse, const float* z_coarse,
+                     const float* raw_fine, const float* z_fine, const float* rng_noise, float* pixels, float* depth,
+                     float* weights_sum, float* weights, int32_t* sort_idx, void* stream) {
+    if (int e = check_render_desc(rd)) return e;
+    FN_REQUIRE(raw_coarse && z_coarse && pixels, "NULL argument");
+    FN_REQUIRE(rd->noise_std == 0.f || rng_noise, "noise_std != 0 needs rng_noise");
+    return composite(rd, out_dim, raw_coarse, z_coarse, raw_fine, z_fine, rd->noise_std != 0.f ? rng_noise : nullptr,
+                     pixels, depth, weights_sum, weights, sort_idx, (cudaStream_t)stream);
+}
+
+size_t fenerf_workspace_bytes(const fenerf_render_desc* rd, const fenerf_field_desc* field) {
+    if (!rd || !field) return 0;
+    return plan_workspace(rd, field->out_dim).total;
+}
+
+int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc* field, const void* packed,
+                          const float* film, const float* x_lin, const float* y_lin, const float* z_lin,
+                          const float* cam2world, const float* rng_perturb, const float* rng_noise_c,
+                          const float* rng_u, const float* rng_noise_f, float* pixels, float* depth,
+                          float* weights_sum, float* weights, int64_t* inds_dbg, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (int e = check_render_desc(rd)) return e;
+    FnLayout L;
+    FN_REQUIRE(fn_make_layout(field, &L) == 0, "unsupported field description");
+    FN_REQUIRE(packed && film && x_lin && y_lin && z_lin && cam2world && rng_perturb && pixels && workspace, "NULL argument");
+    FN_REQUIRE(!rd->hierarchical || rng_u, "hierarchical render needs rng_u");
+    FN_REQUIRE(!rd->hierarchical || rd->num_steps >= 3, "hierarchical render needs num_steps >= 3");
+    FN_REQUIRE(rd->noise_std == 0.f || (rng_noise_f && (!rd->hierarchical || rng_noise_c)), "noise_std != 0 needs the noise draws");
+    FN_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    const int C = L.out_dim;
+    Workspace w = plan_workspace(rd, C);
+    if (workspace_bytes < w.total) return fail(FENERF_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float* points_c = (float*)(ws + w.points_c);
+    float* z_c = (float*)(ws + w.z_c);
+    float* dirs = (float*)(ws + w.dirs);
+    float* origins = (float*)(ws + w.origins);
+    float* raw_c = (float*)(ws + w.raw_c);
+    float* z_f = (float*)(ws + w.z_f);
+    float* points_f = (float*)(ws + w.points_f);
+    float* raw_f = (float*)(ws + w.raw_f);
+    int32_t* guard = (int32_t*)(ws + w.guard);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rays = (long long)rd->img_h * rd->img_w;
+    const long long ppb = rays * rd->num_steps;
+    const float* noise_c = rd->noise_std != 0.f ? rng_noise_c : nullptr;
+    const float* noise_f = rd->noise_std != 0.f ? rng_noise_f : nullptr;
+
+    if (int e = ray_setup(rd, x_lin, y_lin, z_lin, cam2world, rng_perturb, points_c, z_c, dirs, origins, st)) return e;
+    if (int e = run_field(L, packed, points_c, dirs, film, rd->batch, ppb, rd->num_steps, rd->lock_view_dependence,
+                          rd->precision, raw_c, st)) return e;
+    if (rd->precision == FENERF_PRECISION_GUARD) {
+        float tau = rd->guard_tau > 0.f ? rd->guard_tau : 4e-3f;
+        if (int e = guard_refine(L, (const unsigned char*)packed, points_c, dirs, film, rd->batch, rays, rd->num_steps,
+                                 rd->lock_view_dependence, tau, raw_c, guard, st)) return e;
+    }
+    if (rd->hierarchical) {
+        if (int e = resample(rd, C, raw_c, z_c, dirs, origins, noise_c, rng_u, z_f, points_f, (long long*)inds_dbg, st)) return e;
+        if (int e = run_field(L, packed, points_f, dirs, film, rd->batch, ppb, rd->num_steps, rd->lock_view_dependence,
+                              rd->precision, raw_f, st)) return e;
+    }
+    return composite(rd, C, raw_c, z_c, rd->hierarchical ? raw_f : nullptr, rd->hierarchical ? z_f : nullptr, noise_f,
+                     pixels, depth, weights_sum, weights, nullptr, st);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Shared host/device helpers of libfenerf_b200.  Internal.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/fenerf_b200.h"
+#include "layout.h"
+
+namespace fn {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define FN_CUDA_OK(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fn::fail(FENERF_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define FN_LAUNCH_OK(name)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess)                                                                   \
+            return fn::fail(FENERF_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+        fn::count_launch();                                                                      \
+    } while (0)
+
+#define FN_REQUIRE(cond, ...)                                  \
+    do {                                                      \
+        if (!(cond)) return fn::fail(FENERF_E_ARG, __VA_ARGS__); \
+    } while (0)
+
+inline int num_sms() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+// ---- entry points of the individual translation units (called by abi.cu) ----
+int pack_field(const fenerf_field_desc* f, const FnLayout& L, const fenerf_field_params* p, void* packed,
+               cudaStream_t st);
+int siren_points_exact(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
+                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs,
+                       const int32_t* only_idx, int n_only, float* out, cudaStream_t st);
+int siren_points_fast(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
+                      const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
+                      cudaStream_t st);
+int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
+                 const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
+                 float* raw, int32_t* scratch_idx, cudaStream_t st);
+int ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_lin, const float* z_lin,
+              const float* cam2world, const float* rng_perturb, float* points, float* z_vals, float* dirs,
+              float* origins, cudaStream_t st);
+int resample(const fenerf_render_desc* rd, int C, const float* raw, const float* z, const float* dirs,
+             const float* origins, const float* noise, const float* u, float* z_fine, float* pts_fine,
+             long long* inds, cudaStream_t st);
+int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const float* z_c, const float* raw_f,
+              const float* z_f, const float* noise, float* pixels, float* depth, float* wsum, float* weights,
+              int32_t* sort_idx, cudaStream_t st);
+
+}  // namespace fn

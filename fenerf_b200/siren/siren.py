@@ -1,0 +1,303 @@
+"""Host-side mirror of the reference's FiLM-SIREN point networks (siren/siren.py).
+
+Only the module *interface* is kept from the reference -- class names, constructor arguments,
+attribute names, parameter registration order (EMA ``copy_to`` is positional), state-dict keys and
+the init RNG consumption -- so that checkpoints pickled as ``siren.siren.<Class>`` load and the
+reference's callers run unchanged.  The per-point arithmetic is not here: it is the sm_100a CUDA
+kernel behind ``fenerf_siren_points`` (include/fenerf_b200.h).  Each network describes itself to
+the kernel through a small layer table (:class:`FieldSpec`), which is how further reference variants
+can be added without new kernels.
+
+Reference interfaces mirrored (file:line under /root/reference):
+  FiLMLayer                                   siren/siren.py:113-123
+  CustomMappingNetwork                        siren/siren.py:82-102
+  frequency_init / first-layer inits          siren/siren.py:45-49, 104-110, 333-338
+  TALLSIREN                                   siren/siren.py:126-178
+  UniformBoxWarp                              siren/siren.py:181-187
+  sample_from_3dgrid                          siren/siren.py:314-330
+  TextureEmbeddingPiGAN128SEMANTICDISENTANGLE siren/siren.py:1451-1530
+  ...256SEMANTICDISENTANGLE / ..._DIM_96      siren/siren.py:1533-1546
+"""
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+HIDDEN = 256  # the kernels are specialised for 256-wide FiLM layers
+
+
+# --------------------------------------------------------------------------------------------
+# initialisers (same distributions and the same RNG consumption as the reference)
+# --------------------------------------------------------------------------------------------
+def _uniform_weight(bound_of_fan_in):
+    def init(m):
+        if isinstance(m, nn.Linear):
+            with torch.no_grad():
+                b = bound_of_fan_in(m.weight.size(-1))
+                m.weight.uniform_(-b, b)
+    return init
+
+
+def frequency_init(freq):
+    """U(+-sqrt(6/fan_in)/freq) on every nn.Linear weight (siren/siren.py:104-110)."""
+    return _uniform_weight(lambda fan_in: math.sqrt(6 / fan_in) / freq)
+
+
+#: U(+-1/fan_in) first-layer init (siren/siren.py:45-49); fan_in is 3 for every network here,
+#: which also covers ``modified_first_sine_init`` (siren/siren.py:333-338, hard-coded 3).
+first_layer_film_sine_init = _uniform_weight(lambda fan_in: 1 / fan_in)
+modified_first_sine_init = _uniform_weight(lambda fan_in: 1 / 3)
+
+
+def kaiming_leaky_init(m):
+    if m.__class__.__name__.find('Linear') != -1:
+        torch.nn.init.kaiming_normal_(m.weight, a=0.2, mode='fan_in', nonlinearity='leaky_relu')
+
+
+# --------------------------------------------------------------------------------------------
+# building blocks
+# --------------------------------------------------------------------------------------------
+class FiLMLayer(nn.Module):
+    """sin(freq * (x W^T + b) + phase); the state-dict key of the Linear is ``layer``.
+
+    ``forward`` exists for the differentiable torch path only (autograd callers, section 8f-1);
+    the render path never calls it.
+    """
+
+    def __init__(self, input_dim, hidden_dim):
+        super().__init__()
+        self.layer = nn.Linear(input_dim, hidden_dim)
+
+    def forward(self, x, freq, phase_shift):
+        x = self.layer(x)
+        if x.shape[1] != freq.shape[1]:
+            freq = freq.unsqueeze(1).expand_as(x)
+            phase_shift = phase_shift.unsqueeze(1).expand_as(x)
+        return torch.sin(freq * x + phase_shift)
+
+
+class CustomMappingNetwork(nn.Module):
+    """z -> (frequencies, phase_shifts): Linear + LeakyReLU(0.2) x (1 + n_blocks), then Linear.
+
+    Stays in PyTorch/cuBLAS (~0 % of the time).
+    """
+
+    def __init__(self, z_dim, map_hidden_dim, map_output_dim, n_blocks=3):
+        super().__init__()
+        dims = [z_dim] + [map_hidden_dim] * (n_blocks + 1)
+        mods = []
+        for d_in, d_out in zip(dims[:-1], dims[1:]):
+            mods += [nn.Linear(d_in, d_out), nn.LeakyReLU(0.2, inplace=True)]
+        mods.append(nn.Linear(map_hidden_dim, map_output_dim))
+        self.network = nn.Sequential(*mods)
+        self.network.apply(kaiming_leaky_init)
+        with torch.no_grad():
+            self.network[-1].weight *= 0.25
+
+    def forward(self, z):
+        out = self.network(z)
+        half = out.shape[-1] // 2
+        return out[..., :half], out[..., half:]
+
+
+class UniformBoxWarp(nn.Module):
+    def __init__(self, sidelength):
+        super().__init__()
+        self.scale_factor = 2 / sidelength
+
+    def forward(self, coordinates):
+        return coordinates * self.scale_factor
+
+
+def sample_from_3dgrid(coordinates, grid):
+    """Trilinear lookup, align_corners=True, zero padding (siren/siren.py:314-330).
+
+    Torch formulation for the autograd path; the render path uses the channels-last gather in
+    csrc/siren_common.cuh.
+    """
+    coordinates = coordinates.float()
+    grid = grid.float()
+    bsz, n_coords, n_dims = coordinates.shape
+    feats = torch.nn.functional.grid_sample(
+        grid.expand(bsz, -1, -1, -1, -1), coordinates.reshape(bsz, 1, 1, -1, n_dims),
+        mode='bilinear', padding_mode='zeros', align_corners=True)
+    n, c, h, w, d = feats.shape
+    return feats.permute(0, 4, 3, 2, 1).reshape(n, h * w * d, c)
+
+
+# --------------------------------------------------------------------------------------------
+# kernel-facing description of a point network
+# --------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class FieldSpec:
+    """What the CUDA point-network kernels need to know about a FiLM-SIREN field.
+
+    trunk_layers   FiLM layers on the position (first is 3 -> 256, rest 256 -> 256)
+    color_layers   FiLM layers of the colour branch; the first consumes
+                   cat[ray_dir(3), grid_feat(grid_channels), trunk_out(256)]
+    label_dim      semantic logits (0 = none); the reference's activation-free Linear chain
+                   (siren/siren.py:1486-1490) is pre-multiplied into one 256 -> label_dim map
+    grid_channels  feature-grid channels (0 = no grid)
+    input_scale    UniformBoxWarp factor applied to the position before the trunk and the grid
+    out_dim        label_dim + 3 (rgb) + 1 (sigma); channel order [labels, rgb, sigma]
+    """
+    trunk_layers: int
+    color_layers: int
+    label_dim: int
+    grid_channels: int
+    grid_res: int
+    input_scale: float
+    out_dim: int
+    double_latent: bool
+
+
+class _FieldBase(nn.Module):
+    """Shared host logic: FiLM table assembly, weight packing cache, dispatch to the C-ABI."""
+
+    hidden_dim = HIDDEN
+
+    def field_spec(self) -> FieldSpec:  # pragma: no cover - overridden
+        raise NotImplementedError
+
+    # -- packed-weight cache -------------------------------------------------------------
+    def _weights_version(self):
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+
+    def packed(self):
+        """Kernel-layout weights, repacked when any parameter changed in place (optimizer / EMA)."""
+        from .. import packing
+        ver = self._weights_version()
+        cache = self.__dict__.get('_packed_cache')
+        if cache is None or cache[0] != ver:
+            cache = (ver, packing.pack_field(self))
+            self.__dict__['_packed_cache'] = cache
+        return cache[1]
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop('_packed_cache', None)  # never pickle device buffers derived from the weights
+        return state
+
+    # -- the point-network entry the reference's callers use --------------------------------
+    def _render_points(self, points, film, ray_directions):
+        from .. import ops
+        return ops.siren_points(self, points, film, ray_directions)
+
+
+class TALLSIREN(_FieldBase):
+    """pi-GAN's primary SIREN: 8 FiLM + sigma head + 1 colour FiLM + sigmoid rgb (model A)."""
+
+    def __init__(self, input_dim=2, z_dim=100, hidden_dim=256, output_dim=1, device=None):
+        super().__init__()
+        self.device = device
+        self.input_dim = input_dim
+        self.z_dim = z_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+
+        widths = [input_dim] + [hidden_dim] * 8
+        self.network = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        self.final_layer = nn.Linear(hidden_dim, 1)
+        self.color_layer_sine = FiLMLayer(hidden_dim + 3, hidden_dim)
+        self.color_layer_linear = nn.Sequential(nn.Linear(hidden_dim, 3), nn.Sigmoid())
+        self.mapping_network = CustomMappingNetwork(z_dim, 256, (len(self.network) + 1) * hidden_dim * 2)
+
+        for part in (self.network, self.final_layer, self.color_layer_sine, self.color_layer_linear):
+            part.apply(frequency_init(25))
+        self.network[0].apply(first_layer_film_sine_init)
+
+    def field_spec(self):
+        return FieldSpec(trunk_layers=len(self.network), color_layers=1, label_dim=0, grid_channels=0,
+                         grid_res=0, input_scale=1.0, out_dim=4, double_latent=False)
+
+    def film_table(self, frequencies, phase_shifts):
+        """(B, L*256) raw mapping outputs -> (B, L, 2, 256) [15 f + 30, phase] (siren.py:165)."""
+        b = frequencies.shape[0]
+        f = (frequencies * 15 + 30).reshape(b, -1, self.hidden_dim)
+        p = phase_shifts.reshape(b, -1, self.hidden_dim)
+        return torch.stack([f, p], dim=2).float().contiguous()
+
+    def forward(self, input, z, ray_directions, **kwargs):
+        frequencies, phase_shifts = self.mapping_network(z)
+        return self.forward_with_frequencies_phase_shifts(input, frequencies, phase_shifts, ray_directions, **kwargs)
+
+    def forward_with_frequencies_phase_shifts(self, input, frequencies, phase_shifts, ray_directions, **kwargs):
+        return self._render_points(input, self.film_table(frequencies, phase_shifts), ray_directions)
+
+
+class TextureEmbeddingPiGAN128SEMANTICDISENTANGLE(_FieldBase):
+    """Double-latent field: geometry trunk + semantic head, texture branch with a 3-D feature grid
+    (model B).  Output channels: [labels (output_dim-4), rgb (3), sigma (1)]."""
+
+    def __init__(self, input_dim=2, z_geo_dim=100, z_app_dim=100, hidden_dim=128, output_dim=1, device=None):
+        super().__init__()
+        self.device = device
+        self.input_dim = input_dim
+        self.z_geo_dim = z_geo_dim
+        self.z_app_dim = z_app_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+
+        widths = [3] + [hidden_dim] * 8
+        self.network = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        self.final_layer = nn.Linear(hidden_dim, 1)
+        cwidths = [hidden_dim + 32 + 3] + [hidden_dim] * 3
+        self.color_layer_sine = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(cwidths[:-1], cwidths[1:]))
+        self.color_layer_linear = nn.Sequential(nn.Linear(hidden_dim, 3))
+        self.geo_mapping_network = CustomMappingNetwork(z_geo_dim, 256, len(self.network) * hidden_dim * 2)
+        self.app_mapping_network = CustomMappingNetwork(z_app_dim, 256, len(self.color_layer_sine) * hidden_dim * 2)
+        self.label_layer_linear = nn.Sequential(
+            nn.Linear(hidden_dim, hidden_dim), nn.Linear(hidden_dim, hidden_dim),
+            nn.Linear(hidden_dim, self.output_dim - 4))
+
+        for part in (self.network, self.final_layer, self.color_layer_sine, self.color_layer_linear,
+                     self.label_layer_linear):
+            part.apply(frequency_init(25))
+        self.network[0].apply(modified_first_sine_init)
+
+        self.spatial_embeddings = nn.Parameter(torch.randn(1, 32, 96, 96, 96) * 0.01)
+        self.gridwarper = UniformBoxWarp(0.24)
+
+    def field_spec(self):
+        g = self.spatial_embeddings
+        assert g.shape[2] == g.shape[3] == g.shape[4], "cubic feature grid expected"
+        return FieldSpec(trunk_layers=len(self.network), color_layers=len(self.color_layer_sine),
+                         label_dim=self.output_dim - 4, grid_channels=g.shape[1], grid_res=g.shape[2],
+                         input_scale=float(self.gridwarper.scale_factor), out_dim=self.output_dim,
+                         double_latent=True)
+
+    def film_table(self, frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app):
+        """-> (B, L_geo + L_app, 2, 256) [15 f + 30, phase], geometry layers first (siren.py:1510-1511)."""
+        b = frequencies_geo.shape[0]
+        h = self.hidden_dim
+        f = torch.cat([(frequencies_geo * 15 + 30).reshape(b, -1, h), (frequencies_app * 15 + 30).reshape(b, -1, h)], 1)
+        p = torch.cat([phase_shifts_geo.reshape(b, -1, h), phase_shifts_app.reshape(b, -1, h)], 1)
+        return torch.stack([f, p], dim=2).float().contiguous()
+
+    def forward(self, input, z_geo, z_app, ray_directions, **kwargs):
+        frequencies_geo, phase_shifts_geo = self.geo_mapping_network(z_geo)
+        frequencies_app, phase_shifts_app = self.app_mapping_network(z_app)
+        return self.forward_with_frequencies_phase_shifts(
+            input, frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app, ray_directions, **kwargs)
+
+    def forward_with_frequencies_phase_shifts(self, input, frequencies_geo, frequencies_app, phase_shifts_geo,
+                                              phase_shifts_app, ray_directions, **kwargs):
+        film = self.film_table(frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app)
+        return self._render_points(input, film, ray_directions)
+
+
+class TextureEmbeddingPiGAN256SEMANTICDISENTANGLE(TextureEmbeddingPiGAN128SEMANTICDISENTANGLE):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs, hidden_dim=256)
+        self.spatial_embeddings = nn.Parameter(torch.randn(1, 32, 64, 64, 64) * 0.1)
+
+
+class TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96(TextureEmbeddingPiGAN128SEMANTICDISENTANGLE):
+    """The production network of CelebA_double_semantic_texture_embedding_256_dim_96
+    (curriculums.py:159): hidden 256, 32 x 96^3 grid."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs, hidden_dim=256)
+        self.spatial_embeddings = nn.Parameter(torch.randn(1, 32, 96, 96, 96) * 0.1)

@@ -1,0 +1,218 @@
+/*
+ * fenerf_b200 -- C-ABI of the B200-native volumetric face renderer.
+ *
+ * This is the drop-in boundary for the one hot path of MrTornado24/FENeRF: the per-image
+ * volumetric render inside generators.*Generator3d.forward / staged_forward.  The reference has
+ * no FFI on this path (it is ~330 lines of torch ops behind a Python class API), so the entry
+ * points below are what a binding for that path binds: each one replaces a span of the
+ * reference's Python, cited per function (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes; every pointer is a DEVICE pointer unless marked host;
+ *   - the caller owns every buffer; the library never allocates, holds no global state besides a
+ *     thread-local error string, and is re-entrant per stream;
+ *   - all launches go to the given cudaStream_t (passed as void*; NULL = legacy default stream);
+ *   - return 0 on success, a negative FENERF_E_* code otherwise; fenerf_last_error() explains;
+ *   - tensors are contiguous fp32 unless noted; B batch, N = img_h*img_w rays, S = num_steps,
+ *     C = out_dim channels per point ordered [labels.., r, g, b, sigma].
+ *
+ * INTEGRATION.md shows the ctypes stub that binds this header from the reference side.
+ */
+#ifndef FENERF_B200_H
+#define FENERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FENERF_ABI_VERSION 1
+
+/* error codes */
+#define FENERF_OK            0
+#define FENERF_E_ARG        -1   /* bad argument (null pointer, unsupported size, misaligned) */
+#define FENERF_E_UNSUPPORTED -2  /* valid in the reference, not built here (message says what) */
+#define FENERF_E_CUDA       -3   /* a CUDA runtime call failed */
+#define FENERF_E_WORKSPACE  -4   /* workspace too small */
+#define FENERF_E_CLAMP_MODE -5   /* reference raises "Need to choose clamp mode"
+                                    (generators/volumetric_rendering.py:33-34) */
+
+/* ---- point network ("field") --------------------------------------------------------------
+ * Describes a FiLM-SIREN point network of the reference's siren/siren.py family:
+ *   x = pos * input_scale                                 (UniformBoxWarp, siren.py:181-187)
+ *   x = FiLM_0(3->256)(x); x = FiLM_i(256->256)(x), i < trunk_layers      (siren.py:113-123)
+ *   sigma  = Linear(256->1)(x)
+ *   labels = Linear chain 256->256->256->label_dim (no activation; pre-multiplied)   [optional]
+ *   c = FiLM(cat[dir(3), grid_feat(G), x(256)] -> 256); c = FiLM(256->256)(c) ...  color_layers
+ *   rgb = sigmoid(Linear(256->3)(c))
+ *   out = [labels, rgb, sigma]
+ * TALLSIREN (siren.py:126-178):  trunk 8, color 1, label 0, grid 0, scale 1, out 4.
+ * TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96 (siren.py:1451-1546):
+ *                                trunk 8, color 3, label 18, grid 32 x 96^3, scale 2/0.24, out 22.
+ * The hidden width is fixed at 256.                                                            */
+#define FENERF_MAX_TRUNK 8
+#define FENERF_MAX_COLOR 4
+#define FENERF_MAX_LABEL 32
+#define FENERF_HIDDEN 256
+
+typedef struct fenerf_field_desc {
+    int32_t trunk_layers;   /* 2..8 */
+    int32_t color_layers;   /* 1..4 */
+    int32_t label_dim;      /* 0..32 */
+    int32_t grid_channels;  /* 0 or 32 */
+    int32_t grid_res;       /* cubic grid side (D = H = W), 0 if no grid */
+    int32_t out_dim;        /* label_dim + 4 */
+    float   input_scale;
+    int32_t reserved;
+} fenerf_field_desc;
+
+/* Raw parameters exactly as torch stores them: nn.Linear.weight is [out][in] row-major fp32,
+ * bias [out]; grid is the reference's channel-major (1, G, D, H, W) tensor (siren.py:1546). */
+typedef struct fenerf_field_params {
+    const float* trunk_w[FENERF_MAX_TRUNK];  /* [256][3] then [256][256] */
+    const float* trunk_b[FENERF_MAX_TRUNK];
+    const float* sigma_w;                    /* [1][256] */
+    const float* sigma_b;                    /* [1] */
+    const float* color_w[FENERF_MAX_COLOR];  /* first [256][3+G+256] (cat order dir, feat, x), rest [256][256] */
+    const float* color_b[FENERF_MAX_COLOR];
+    const float* rgb_w;                      /* [3][256] */
+    const float* rgb_b;                      /* [3] */
+    const float* label_w[3];                 /* [256][256], [256][256], [label_dim][256]; NULL if label_dim == 0 */
+    const float* label_b[3];
+    const float* grid;                       /* (1, G, R, R, R) or NULL */
+} fenerf_field_params;
+
+/* Bytes of the packed, kernel-layout copy of a field's parameters. */
+size_t fenerf_packed_bytes(const fenerf_field_desc* field);
+
+/* Re-lays the raw parameters out for the kernels (k-major fp32 for the exact path, UMMA
+ * 128B-swizzled fp16 images for the tcgen05 path, pre-multiplied label chain, channels-last
+ * grid).  Call again whenever the parameters change (optimizer step, EMA copy_to).
+ * `packed` must be 1024-byte aligned. */
+int fenerf_pack_field(const fenerf_field_desc* field, const fenerf_field_params* params,
+                      void* packed, size_t packed_bytes, void* stream);
+
+/* precision modes of the point network */
+#define FENERF_PRECISION_EXACT 0  /* fp32 FFMA + precise sinf everywhere (CUDA cores)            */
+#define FENERF_PRECISION_FAST  1  /* fp16 operands / fp32 accumulate on tcgen05, sin.approx      */
+#define FENERF_PRECISION_GUARD 2  /* FAST, then EXACT re-evaluation of the far sample of every ray
+                                     whose |sigma| < guard_tau (the reference's delta=1e10 step,
+                                     volumetric_rendering.py:24,32) -- the default                */
+
+/* Evaluates the field at arbitrary points.
+ * Replaces <SIREN>.forward_with_frequencies_phase_shifts (siren/siren.py:164-178, 1509-1530);
+ * also the entry extract_*shapes.py needs (extract_double_semantic_shapes.py:59,80).
+ *   points  (B, P, 3)      positions, not yet box-warped
+ *   dirs    (B, P/dir_group, 3)  one direction per `dir_group` consecutive points (1 = per point)
+ *   film    (B, trunk+color, 2, 256)  [15*freq+30, phase] per FiLM layer
+ *   out     (B, P, C)
+ *   only_idx  optional int32 list (n_only entries) of flat point indices b*P+p to evaluate;
+ *             others are left untouched in `out` (used by the GUARD refinement)               */
+int fenerf_siren_points(const fenerf_field_desc* field, const void* packed,
+                        const float* points, const float* dirs, const float* film,
+                        int32_t batch, int64_t points_per_batch, int32_t dir_group,
+                        int32_t precision, const int32_t* only_idx, int32_t n_only,
+                        float* out, void* stream);
+
+/* ---- render ------------------------------------------------------------------------------ */
+#define FENERF_CLAMP_RELU 0
+#define FENERF_CLAMP_SOFTPLUS 1
+
+/* fill_mode of fancy_integration (generators/volumetric_rendering.py:53-102) */
+#define FENERF_FILL_NONE 0
+#define FENERF_FILL_DEBUG 1
+#define FENERF_FILL_WEIGHT 2
+#define FENERF_FILL_WEIGHT_DEBUG 3
+#define FENERF_FILL_SEG_PADDING_BACKGROUND 4
+#define FENERF_FILL_EVAL_SEG_PADDING_BACKGROUND 5
+#define FENERF_FILL_EVAL_WHITE_BACK 6
+
+/* fill_color as the value written to the non-background channels: black 0, white 1, grey 0.5,
+ * light_grey 0.81 (volumetric_rendering.py:74-81); negative = "no such colour" (pixels untouched) */
+
+typedef struct fenerf_render_desc {
+    int32_t batch;
+    int32_t img_h, img_w;       /* reference always renders square; kept separate for clarity */
+    int32_t num_steps;          /* S, coarse samples per ray (2..64) */
+    int32_t hierarchical;       /* 1: resample S fine points per ray (generators.py:58-89) */
+    int32_t clamp_mode;         /* FENERF_CLAMP_* ; anything else -> FENERF_E_CLAMP_MODE */
+    int32_t last_back, white_back, black_back;
+    int32_t fill_mode;          /* FENERF_FILL_* (staged_forward only) */
+    float   fill_color;
+    int32_t softmax_label;      /* softmax over the label channels of the composited pixel */
+    int32_t lock_view_dependence; /* every direction := (0, 0, -1) (generators.py:50-52) */
+    int32_t precision;          /* FENERF_PRECISION_* */
+    float   noise_std;          /* nerf_noise */
+    float   tan_half_fov;       /* (float) tan(2*pi*fov/360 / 2), volumetric_rendering.py:119 */
+    float   guard_tau;          /* GUARD threshold on |sigma_far| (default 4e-3 if <= 0) */
+} fenerf_render_desc;
+
+/* Camera rays, stratified perturbation and camera-to-world transform.
+ * Replaces get_initial_rays_trig + perturb_points + the three bmm of transform_sampled_points
+ * (generators/volumetric_rendering.py:109-168).
+ *   x_lin (W) = linspace(-1,1,W); y_lin (H) = linspace(1,-1,H); z_lin (S) = linspace(near,far,S)
+ *   cam2world (B,16) row-major 4x4 (create_cam2world_matrix, :230-248)
+ *   rng_perturb (B,N,S) uniform [0,1) draw #1 (torch.rand, :135)
+ * out: points (B,N,S,3) world space; z_vals (B,N,S); dirs (B,N,3) world; origins (B,3)        */
+int fenerf_ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_lin,
+                     const float* z_lin, const float* cam2world, const float* rng_perturb,
+                     float* points, float* z_vals, float* dirs, float* origins, void* stream);
+
+/* Coarse weights + inverse-CDF resampling + fine points.
+ * Replaces fancy_integration(coarse) -> weights, the resample prep and sample_pdf
+ * (generators/generators.py:59-74; volumetric_rendering.py:18-38, 259-300).
+ *   raw_coarse (B,N,S,C) (sigma = last channel); z_vals (B,N,S)
+ *   rng_noise (B,N,S) normal draw #4 or NULL (treated as 0; required if noise_std != 0)
+ *   rng_u (B*N,S) uniform draw #5
+ * out: z_fine (B,N,S); points_fine (B,N,S,3); inds (B*N,S) int64 searchsorted result or NULL */
+int fenerf_resample(const fenerf_render_desc* rd, int32_t out_dim, const float* raw_coarse,
+                    const float* z_vals, const float* dirs, const float* origins,
+                    const float* rng_noise, const float* rng_u,
+                    float* z_fine, float* points_fine, int64_t* inds, void* stream);
+
+/* Merge-sort of coarse + fine samples, alpha compositing, fill modes, NCHW epilogue.
+ * Replaces cat/sort/gather (generators/generators.py:85-89), the final fancy_integration
+ * (volumetric_rendering.py:18-106) and the softmax / permute / *2-1 epilogue (:97-104).
+ *   raw_fine / z_fine may be NULL when !hierarchical
+ *   rng_noise (B,N,S') normal draw #6 (S' = 2S if hierarchical) or NULL
+ * out: pixels (B, C_img, H, W) already *2-1, C_img = C-1 (+1 for the seg_padding fill modes)
+ *      depth (B,N) or NULL;  weights_sum (B,N) or NULL;  weights (B,N,S') or NULL
+ *      sort_idx (B,N,S') int32 merge order or NULL (debug / parity)                           */
+int fenerf_composite(const fenerf_render_desc* rd, int32_t out_dim, const float* raw_coarse,
+                     const float* z_coarse, const float* raw_fine, const float* z_fine,
+                     const float* rng_noise, float* pixels, float* depth, float* weights_sum,
+                     float* weights, int32_t* sort_idx, void* stream);
+
+/* Scratch bytes fenerf_render_forward needs for this (render, field) pair. */
+size_t fenerf_workspace_bytes(const fenerf_render_desc* rd, const fenerf_field_desc* field);
+
+/* The whole per-batch render: ray_setup -> field(coarse) -> resample -> field(fine) -> composite.
+ * Replaces the body of ImplicitGenerator3d.forward / DoubleImplicitGenerator3d.forward after the
+ * mapping network (generators/generators.py:41-104, 465-527) and the chunked loops of
+ * staged_forward* (:154-233, 569-646).
+ *   rng_perturb (B,N,S) #1, rng_noise_c (B,N,S) #4 or NULL, rng_u (B*N,S) #5,
+ *   rng_noise_f (B,N,2S) #6 or NULL  -- the caller draws them in the reference's order
+ * out as fenerf_composite; inds_dbg as fenerf_resample.                                        */
+int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc* field,
+                          const void* packed, const float* film,
+                          const float* x_lin, const float* y_lin, const float* z_lin,
+                          const float* cam2world,
+                          const float* rng_perturb, const float* rng_noise_c,
+                          const float* rng_u, const float* rng_noise_f,
+                          float* pixels, float* depth, float* weights_sum, float* weights,
+                          int64_t* inds_dbg, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* Per-thread message for the last non-zero return. */
+const char* fenerf_last_error(void);
+
+/* ABI version and a counter of kernels launched by this library since load (bench evidence). */
+int32_t fenerf_abi_version(void);
+int64_t fenerf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FENERF_B200_H */
