@@ -1,0 +1,236 @@
+"""Thin Python operators over the C-ABI (include/fenerf_b200.h).
+
+Everything here is plumbing: validate tensors (device / dtype / contiguity, in the style of the
+reference's own extension shim siren/op/fused_bias_act.cpp:7-9), hand raw device pointers and the
+current CUDA stream to the library, wrap the outputs.  No arithmetic of the hot path happens in
+Python or in torch ops.
+"""
+import ctypes as C
+import math
+import os
+
+import torch
+
+from . import _lib
+
+_DEFAULT_PRECISION = os.environ.get("FENERF_B200_PRECISION", "guard")
+
+
+def default_precision():
+    return _DEFAULT_PRECISION
+
+
+def set_default_precision(name):
+    global _DEFAULT_PRECISION
+    if name not in _lib.PRECISION:
+        raise ValueError("precision must be one of %s" % sorted(_lib.PRECISION))
+    _DEFAULT_PRECISION = name
+
+
+def _precision_code(precision):
+    name = precision if precision is not None else _DEFAULT_PRECISION
+    if isinstance(name, int):
+        return name
+    return _lib.PRECISION[name]
+
+
+def _chk(t, name, device=None, dtype=torch.float32):
+    if t is None:
+        return 0
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (fenerf_b200 has no CPU path)" % name)
+    if device is not None and t.device != device:
+        raise RuntimeError("%s is on %s, expected %s" % (name, t.device, device))
+    if t.dtype != dtype:
+        raise RuntimeError("%s must be %s (got %s)" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    return t.data_ptr()
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _prep(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def make_render_desc(*, batch, img_size, num_steps, hierarchical, clamp_mode, nerf_noise, fov, last_back=False,
+                     white_back=False, black_back=False, fill_mode=None, fill_color="black", softmax_label=False,
+                     lock_view_dependence=False, precision=None, guard_tau=0.0):
+    if fill_mode not in _lib.FILL_MODE:
+        raise ValueError("unknown fill_mode %r" % (fill_mode,))
+    # the reference evaluates np.tan((2*pi*fov/360)/2) in double and divides a float32 tensor by it
+    tan_half = math.tan((2 * math.pi * fov / 360) / 2)
+    return _lib.RenderDesc(
+        batch=batch, img_h=img_size, img_w=img_size, num_steps=num_steps, hierarchical=int(bool(hierarchical)),
+        clamp_mode=_lib.CLAMP.get(clamp_mode, -1), last_back=int(bool(last_back)), white_back=int(bool(white_back)),
+        black_back=int(bool(black_back)), fill_mode=_lib.FILL_MODE[fill_mode],
+        fill_color=_lib.FILL_COLOR.get(fill_color, -1.0), softmax_label=int(bool(softmax_label)),
+        lock_view_dependence=int(bool(lock_view_dependence)), precision=_precision_code(precision),
+        noise_std=float(nerf_noise), tan_half_fov=tan_half, guard_tau=float(guard_tau))
+
+
+# --------------------------------------------------------------------------------------------
+# point network
+# --------------------------------------------------------------------------------------------
+def siren_points(module, points, film, ray_directions, precision=None, dir_group=None, only_idx=None):
+    """(B,P,3) points, (B,L,2,256) FiLM table, (B,P,3) or (B,P/g,3) directions -> (B,P,C).
+
+    The entry behind <SIREN>.forward_with_frequencies_phase_shifts (siren/siren.py:164-178,
+    1509-1530).  Forward-only: differentiating through it is section 8f-1 of SURVEY.md.
+    """
+    if needs_grad(module, points, film):
+        if autograd_opted_in():
+            from . import autograd_path
+            return autograd_path.siren_points_torch(module, points, film, ray_directions)
+        raise NotImplementedError(GRAD_MESSAGE)
+    packed = module.packed()
+    device = packed.device
+    pts = _prep(points, device)
+    flm = _prep(film, device)
+    dirs = _prep(ray_directions, device)
+    b, p, _ = pts.shape
+    if dir_group is None:
+        if dirs.shape[1] == p:
+            dir_group = 1
+        else:
+            if p % dirs.shape[1]:
+                raise ValueError("ray_directions (%d) does not divide the point count (%d)" % (dirs.shape[1], p))
+            dir_group = p // dirs.shape[1]
+    if flm.shape[0] != b or flm.shape[2:] != (2, _lib.HIDDEN):
+        raise ValueError("film table has shape %s" % (tuple(flm.shape),))
+    out = torch.empty((b, p, packed.desc.out_dim), dtype=torch.float32, device=device) if only_idx is None else only_idx[1]
+    idx_ptr, n_only = 0, 0
+    if only_idx is not None:
+        idx = only_idx[0]
+        idx_ptr, n_only = _chk(idx, "only_idx", device, torch.int32), idx.numel()
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().fenerf_siren_points(
+            C.byref(packed.desc), packed.ptr, _chk(pts, "points"), _chk(dirs, "ray_directions"), _chk(flm, "film"),
+            b, p, dir_group, _precision_code(precision), idx_ptr, n_only, _chk(out, "out"), _stream(device)))
+    return out
+
+
+GRAD_MESSAGE = ("fenerf_b200: backward through the fused render is not built yet (SURVEY.md 8f-1); wrap the call "
+                "in torch.no_grad(), or set FENERF_B200_TORCH_AUTOGRAD=1 to route grad-requiring calls through "
+                "the torch-op formulation (fenerf_b200/autograd_path.py)")
+
+
+def autograd_opted_in():
+    return os.environ.get("FENERF_B200_TORCH_AUTOGRAD", "0") == "1"
+
+
+def needs_grad(module, *tensors):
+    """True when the caller expects autograd to flow through the point network."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+# --------------------------------------------------------------------------------------------
+# render stages (exposed for stage-level parity tests and for callers that bring their own rays)
+# --------------------------------------------------------------------------------------------
+def ray_setup(rd, x_lin, y_lin, z_lin, cam2world, rng_perturb):
+    device = cam2world.device
+    b, n, s = rd.batch, rd.img_h * rd.img_w, rd.num_steps
+    points = torch.empty((b, n, s, 3), dtype=torch.float32, device=device)
+    z_vals = torch.empty((b, n, s, 1), dtype=torch.float32, device=device)
+    dirs = torch.empty((b, n, 3), dtype=torch.float32, device=device)
+    origins = torch.empty((b, 3), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().fenerf_ray_setup(
+            C.byref(rd), _chk(x_lin, "x_lin", device), _chk(y_lin, "y_lin", device), _chk(z_lin, "z_lin", device),
+            _chk(cam2world, "cam2world", device), _chk(rng_perturb, "rng_perturb", device),
+            points.data_ptr(), z_vals.data_ptr(), dirs.data_ptr(), origins.data_ptr(), _stream(device)))
+    return points, z_vals, dirs, origins
+
+
+def resample(rd, raw_coarse, z_vals, dirs, origins, rng_noise, rng_u, want_inds=False):
+    device = raw_coarse.device
+    b, n, s = rd.batch, rd.img_h * rd.img_w, rd.num_steps
+    c = raw_coarse.shape[-1]
+    z_fine = torch.empty((b, n, s, 1), dtype=torch.float32, device=device)
+    pts = torch.empty((b, n, s, 3), dtype=torch.float32, device=device)
+    inds = torch.empty((b * n, s), dtype=torch.int64, device=device) if want_inds else None
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().fenerf_resample(
+            C.byref(rd), c, _chk(raw_coarse, "raw_coarse", device), _chk(z_vals, "z_vals", device),
+            _chk(dirs, "dirs", device), _chk(origins, "origins", device), _chk(rng_noise, "rng_noise", device),
+            _chk(rng_u, "rng_u", device), z_fine.data_ptr(), pts.data_ptr(),
+            inds.data_ptr() if inds is not None else 0, _stream(device)))
+    return z_fine, pts, inds
+
+
+def composite(rd, raw_coarse, z_coarse, raw_fine=None, z_fine=None, rng_noise=None, want_weights=False,
+              want_sort_idx=False):
+    device = raw_coarse.device
+    b, n, s = rd.batch, rd.img_h * rd.img_w, rd.num_steps
+    c = raw_coarse.shape[-1]
+    ns = 2 * s if rd.hierarchical else s
+    pad = rd.fill_mode in (_lib.FILL_MODE["seg_padding_background"], _lib.FILL_MODE["eval_seg_padding_background"])
+    c_img = c - 1 + (1 if pad else 0)
+    pixels = torch.empty((b, c_img, rd.img_h, rd.img_w), dtype=torch.float32, device=device)
+    depth = torch.empty((b, n, 1), dtype=torch.float32, device=device)
+    wsum = torch.empty((b, n, 1), dtype=torch.float32, device=device)
+    weights = torch.empty((b, n, ns, 1), dtype=torch.float32, device=device) if want_weights else None
+    sidx = torch.empty((b, n, ns), dtype=torch.int32, device=device) if want_sort_idx else None
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().fenerf_composite(
+            C.byref(rd), c, _chk(raw_coarse, "raw_coarse", device), _chk(z_coarse, "z_coarse", device),
+            _chk(raw_fine, "raw_fine", device), _chk(z_fine, "z_fine", device), _chk(rng_noise, "rng_noise", device),
+            pixels.data_ptr(), depth.data_ptr(), wsum.data_ptr(), weights.data_ptr() if weights is not None else 0,
+            sidx.data_ptr() if sidx is not None else 0, _stream(device)))
+    return pixels, depth, wsum, weights, sidx
+
+
+_WORKSPACES = {}
+
+
+def _workspace(device, nbytes):
+    """One grow-only scratch buffer per (device, stream): the C-ABI never allocates."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.05) + 256, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def render_forward(module, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb, rng_noise_c, rng_u, rng_noise_f,
+                   want_depth=True, want_weights_sum=True, want_weights=False, want_inds=False):
+    """One call into fenerf_render_forward: the whole render after the mapping network."""
+    packed = module.packed()
+    device = packed.device
+    lib = _lib.lib()
+    b, n, s = rd.batch, rd.img_h * rd.img_w, rd.num_steps
+    ns = 2 * s if rd.hierarchical else s
+    c = packed.desc.out_dim
+    pad = rd.fill_mode in (_lib.FILL_MODE["seg_padding_background"], _lib.FILL_MODE["eval_seg_padding_background"])
+    c_img = c - 1 + (1 if pad else 0)
+    film = _prep(film, device)
+    if film.shape != (b, packed.desc.trunk_layers + packed.desc.color_layers, 2, _lib.HIDDEN):
+        raise ValueError("film table has shape %s" % (tuple(film.shape),))
+    pixels = torch.empty((b, c_img, rd.img_h, rd.img_w), dtype=torch.float32, device=device)
+    depth = torch.empty((b, n, 1), dtype=torch.float32, device=device) if want_depth else None
+    wsum = torch.empty((b, n, 1), dtype=torch.float32, device=device) if want_weights_sum else None
+    weights = torch.empty((b, n, ns, 1), dtype=torch.float32, device=device) if want_weights else None
+    inds = torch.empty((b * n, s), dtype=torch.int64, device=device) if (want_inds and rd.hierarchical) else None
+    with torch.cuda.device(device):
+        nbytes = lib.fenerf_workspace_bytes(C.byref(rd), C.byref(packed.desc))
+        ws = _workspace(device, nbytes)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        _lib.check(lib.fenerf_render_forward(
+            C.byref(rd), C.byref(packed.desc), packed.ptr, _chk(film, "film", device),
+            _chk(x_lin, "x_lin", device), _chk(y_lin, "y_lin", device), _chk(z_lin, "z_lin", device),
+            _chk(cam2world, "cam2world", device), _chk(rng_perturb, "rng_perturb", device),
+            _chk(rng_noise_c, "rng_noise_c", device), _chk(rng_u, "rng_u", device),
+            _chk(rng_noise_f, "rng_noise_f", device),
+            pixels.data_ptr(), depth.data_ptr() if depth is not None else 0,
+            wsum.data_ptr() if wsum is not None else 0, weights.data_ptr() if weights is not None else 0,
+            inds.data_ptr() if inds is not None else 0, ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()),
+            _stream(device)))
+    return pixels, depth, wsum, weights, inds

@@ -1,0 +1,87 @@
+"""Host glue between a field module (fenerf_b200.siren.siren) and ``fenerf_pack_field``.
+
+Collects the raw ``nn.Parameter`` device pointers into ``fenerf_field_params`` and lets the library
+re-lay them out on the device; PyTorch only owns the memory.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class PackedField:
+    desc: "_lib.FieldDesc"
+    buffer: torch.Tensor      # owning uint8 allocation
+    ptr: int                  # 1024-byte aligned device pointer inside `buffer`
+    nbytes: int
+    device: torch.device
+
+
+def field_desc(spec) -> "_lib.FieldDesc":
+    return _lib.FieldDesc(trunk_layers=spec.trunk_layers, color_layers=spec.color_layers, label_dim=spec.label_dim,
+                          grid_channels=spec.grid_channels, grid_res=spec.grid_res, out_dim=spec.out_dim,
+                          input_scale=spec.input_scale, reserved=0)
+
+
+def _f32(t, device):
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.device != device:
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+def collect_params(module, device):
+    """-> (FieldParams, keepalive list). Parameter order / names per SURVEY.md section 8b."""
+    spec = module.field_spec()
+    if getattr(module, "hidden_dim", 256) != _lib.HIDDEN:
+        raise ValueError("the sm_100a kernels are specialised for hidden_dim=256 (got %s)" % module.hidden_dim)
+    keep = []
+
+    def ptr(t):
+        t = _f32(t, device)
+        keep.append(t)
+        return t.data_ptr()
+
+    p = _lib.FieldParams()
+    for i, layer in enumerate(module.network):
+        p.trunk_w[i] = ptr(layer.layer.weight)
+        p.trunk_b[i] = ptr(layer.layer.bias)
+    p.sigma_w = ptr(module.final_layer.weight)
+    p.sigma_b = ptr(module.final_layer.bias)
+    color = module.color_layer_sine
+    color = list(color) if isinstance(color, torch.nn.ModuleList) else [color]
+    for i, layer in enumerate(color):
+        p.color_w[i] = ptr(layer.layer.weight)
+        p.color_b[i] = ptr(layer.layer.bias)
+    p.rgb_w = ptr(module.color_layer_linear[0].weight)
+    p.rgb_b = ptr(module.color_layer_linear[0].bias)
+    if spec.label_dim:
+        for i in range(3):
+            p.label_w[i] = ptr(module.label_layer_linear[i].weight)
+            p.label_b[i] = ptr(module.label_layer_linear[i].bias)
+    if spec.grid_channels:
+        p.grid = ptr(module.spatial_embeddings)
+    return p, keep
+
+
+def pack_field(module) -> PackedField:
+    lib = _lib.lib()
+    device = next(module.parameters()).device
+    if device.type != "cuda":
+        raise RuntimeError("fenerf_b200 renders on CUDA only; move the generator to a B200 (got %s)" % device)
+    spec = module.field_spec()
+    desc = field_desc(spec)
+    nbytes = lib.fenerf_packed_bytes(C.byref(desc))
+    if nbytes == 0:
+        _lib.check(-1)
+    with torch.cuda.device(device):
+        buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        ptr = (buf.data_ptr() + 1023) // 1024 * 1024
+        params, keep = collect_params(module, device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(lib.fenerf_pack_field(C.byref(desc), C.byref(params), ptr, nbytes, stream))
+        del keep
+    return PackedField(desc=desc, buffer=buf, ptr=ptr, nbytes=nbytes, device=device)

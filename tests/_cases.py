@@ -1,0 +1,116 @@
+"""Parity cases shared by the golden generator, the oracle tests and the GPU parity tests."""
+import math
+import os
+import sys
+from dataclasses import dataclass, field
+from functools import lru_cache
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# constants of the named curricula (curriculums.py:139-146, 164)
+BASE = dict(fov=12, ray_start=0.88, ray_end=1.12, h_mean=math.pi * 0.5, v_mean=math.pi * 0.5, clamp_mode='relu',
+            last_back=False, hierarchical_sample=True, sample_dist='gaussian')
+
+
+@dataclass(frozen=True)
+class Case:
+    name: str
+    model: str                     # "A" = ImplicitGenerator3d + TALLSIREN, "B" = Double + TexEmb_DIM_96
+    batch: int
+    seed: int
+    cfg: dict = field(default_factory=dict)
+    method: str = "forward"        # or "staged_forward"
+    sigma_bias_shift: float = 0.0  # final_layer.bias += shift (opaque-regime fixture)
+    psi: float = 1.0
+
+
+def _cfg(**kw):
+    d = dict(BASE)
+    d.update(kw)
+    return d
+
+
+CASES = [
+    # parity runs keep the camera at the mean pose unless stated
+    Case("a_small", "A", 2, 11, _cfg(img_size=16, num_steps=12, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("a_small_noise", "A", 2, 12, _cfg(img_size=16, num_steps=12, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.4)),
+    Case("a_small_opaque", "A", 1, 13, _cfg(img_size=16, num_steps=12, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                            white_back=True), sigma_bias_shift=0.5),
+    Case("a_nohier_softplus", "A", 1, 14, _cfg(img_size=16, num_steps=8, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                               hierarchical_sample=False, clamp_mode='softplus', last_back=True)),
+    Case("a_lockview_uniform", "A", 1, 15, _cfg(img_size=12, num_steps=9, h_stddev=0.2, v_stddev=0.1, nerf_noise=0.0,
+                                                sample_dist='uniform', lock_view_dependence=True, black_back=True)),
+    Case("a_cfg1", "A", 1, 16, _cfg(img_size=64, num_steps=12, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0)),
+    Case("a_staged_white", "A", 1, 17, _cfg(img_size=16, num_steps=12, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                            fill_mode='eval_white_back'), method="staged_forward", psi=0.7),
+    Case("b_small", "B", 1, 21, _cfg(img_size=16, num_steps=12, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("b_small_opaque", "B", 1, 22, _cfg(img_size=12, num_steps=10, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0),
+         sigma_bias_shift=0.5),
+    Case("b_staged_segpad", "B", 1, 23, _cfg(img_size=16, num_steps=12, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                             fill_mode='seg_padding_background', fill_color='grey'),
+         method="staged_forward", psi=0.7),
+]
+CASE_BY_NAME = {c.name: c for c in CASES}
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_path(case):
+    return os.path.join(GOLDEN_DIR, case.name + ".npz")
+
+
+def apply_weight_edits(gen, case):
+    if case.sigma_bias_shift:
+        with torch.no_grad():
+            gen.siren.final_layer.bias += case.sigma_bias_shift
+
+
+def make_latents(case):
+    """latent i of the batch = randn(1, 256) under manual_seed(1000 + i); model B: geo then app."""
+    zs = []
+    for i in range(case.batch):
+        torch.manual_seed(1000 + i)
+        zs.append([torch.randn(1, 256) for _ in range(1 if case.model == "A" else 2)])
+    return tuple(torch.cat([z[j] for z in zs], 0) for j in range(len(zs[0])))
+
+
+def reference_kwargs(case):
+    kw = dict(case.cfg)
+    if case.method == "staged_forward":
+        kw["psi"] = case.psi
+        kw["max_batch_size"] = 2400000
+    return kw
+
+
+@lru_cache(maxsize=2)
+def _mirror_generator_cached(model, softmax_label):
+    from fenerf_b200.generators import generators as g
+    from fenerf_b200.siren import siren as s
+    torch.manual_seed(0)
+    if model == "A":
+        gen = g.ImplicitGenerator3d(s.TALLSIREN, 256, 4, softmax_label=softmax_label)
+    else:
+        gen = g.DoubleImplicitGenerator3d(s.TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96, 256, 256, 22,
+                                          softmax_label=softmax_label)
+    gen.eval()
+    return gen
+
+
+def build_mirror(case, device="cpu"):
+    """Our mirror classes, constructed under the same seed protocol as the reference; returns a fresh
+    deep copy so that weight edits and device moves do not leak between tests."""
+    import copy
+    gen = copy.deepcopy(_mirror_generator_cached(case.model, bool(case.cfg.get("softmax_label", False))))
+    apply_weight_edits(gen, case)
+    gen.to(device)
+    gen.device = device
+    gen.siren.device = device
+    return gen
+
+
+def avg_film_draws(case):
+    """The generate_avg_frequencies draws a staged_forward makes first (generators.py:142, 554)."""
+    return [torch.randn(10000, 256) for _ in range(1 if case.model == "A" else 2)]

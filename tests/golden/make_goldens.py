@@ -1,0 +1,81 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (needs /root/reference).
+
+    python tests/golden/make_goldens.py
+
+The reference holds no golden vectors for the render path, so the pin of the
+oracle is the reference's own forward on fixed seeds, captured here.  Run in the build container
+only; the .npz files travel with the repo, /root/reference does not.
+
+Seed protocol (shared with tests/_cases.py):
+  torch.manual_seed(0)            -> construct the generator (reference init order)
+  generator.set_device('cpu')     -> consumes the generate_avg_frequencies draws
+  [case-specific weight edits, e.g. final_layer.bias += 0.5]
+  torch.manual_seed(1000 + i)     -> latent i = randn(1, 256)    (geo, then app for model B)
+  torch.manual_seed(case.seed)    -> the forward under test
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import ref_shim  # noqa: E402
+import _cases  # noqa: E402
+
+
+def state_digest(module):
+    h = hashlib.sha256()
+    for k, v in module.state_dict().items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def build_reference(case, ref_generators, ref_siren):
+    torch.manual_seed(0)
+    if case.model == "A":
+        gen = ref_generators.ImplicitGenerator3d(ref_siren.TALLSIREN, 256, 4, softmax_label=case.cfg.get("softmax_label", False))
+    else:
+        gen = ref_generators.DoubleImplicitGenerator3d(
+            ref_siren.TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96, 256, 256, 22,
+            softmax_label=case.cfg.get("softmax_label", False))
+    gen.set_device("cpu")
+    gen.eval()
+    digest = state_digest(gen)
+    _cases.apply_weight_edits(gen, case)
+    return gen, digest
+
+
+def main():
+    ref_generators, ref_siren, _ = ref_shim.load()
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for case in _cases.CASES:
+        gen, digest = build_reference(case, ref_generators, ref_siren)
+        latents = _cases.make_latents(case)
+        kw = _cases.reference_kwargs(case)
+        torch.manual_seed(case.seed)
+        with torch.no_grad():
+            if case.method == "forward":
+                pixels, poses = gen(*latents, **kw)
+                extra = {"poses": poses.numpy()}
+            elif case.method == "staged_forward":
+                res = gen.staged_forward(*latents, **kw)
+                pixels = res[0]
+                extra = {"depth_map": res[1].numpy()}
+                if len(res) > 2:
+                    extra["third"] = res[2].numpy()
+            else:
+                raise ValueError(case.method)
+        path = os.path.join(out_dir, case.name + ".npz")
+        np.savez_compressed(path, pixels=pixels.cpu().numpy(), state_digest=np.array(digest), **extra)
+        print("%-28s pixels %s  mean|x| %.6f  -> %s (%.1f KB)" % (
+            case.name, tuple(pixels.shape), float(pixels.abs().mean()), os.path.basename(path), os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()
