@@ -100,9 +100,9 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
         self.siren.device = device
         self.generate_avg_frequencies()
 
-    def generate_avg_frequencies(self):
+    def generate_avg_frequencies(self, rng=None):
         """Mean FiLM parameters over 10 000 latents (generators.py:121-129); consumes randn(10000, z)."""
-        z = torch.randn((10000, self.z_dim), device=self.siren.device)
+        z = rng.randn(10000, self.z_dim) if rng is not None else torch.randn((10000, self.z_dim), device=self.siren.device)
         with torch.no_grad():
             frequencies, phase_shifts = self.siren.mapping_network(z)
         self.avg_frequencies = frequencies.mean(0, keepdim=True)
@@ -135,7 +135,7 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
             img_size = kwargs['img_feat_size']
         self._check_no_neural_renderer()
         batch_size = z.shape[0]
-        self.generate_avg_frequencies()
+        self.generate_avg_frequencies(rng=kwargs.get('_avg_rng'))
         with torch.no_grad():
             raw_frequencies, raw_phase_shifts = self.siren.mapping_network(z)
             frequencies = self.avg_frequencies + psi * (raw_frequencies - self.avg_frequencies)
@@ -202,10 +202,13 @@ class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
         self.siren.device = device
         self.generate_avg_frequencies()
 
-    def generate_avg_frequencies(self):
+    def generate_avg_frequencies(self, rng=None):
         """generators.py:530-543; consumes randn(10000, z_geo) then randn(10000, z_app)."""
-        z_geo = torch.randn((10000, self.z_geo_dim), device=self.siren.device)
-        z_app = torch.randn((10000, self.z_app_dim), device=self.siren.device)
+        if rng is not None:
+            z_geo, z_app = rng.randn(10000, self.z_geo_dim), rng.randn(10000, self.z_app_dim)
+        else:
+            z_geo = torch.randn((10000, self.z_geo_dim), device=self.siren.device)
+            z_app = torch.randn((10000, self.z_app_dim), device=self.siren.device)
         with torch.no_grad():
             frequencies_geo, phase_shifts_geo = self.siren.geo_mapping_network(z_geo)
             frequencies_app, phase_shifts_app = self.siren.app_mapping_network(z_app)
@@ -243,7 +246,7 @@ class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
                        v_mean, psi=1, lock_view_dependence=False, max_batch_size=50000, depth_map=False, near_clip=0,
                        far_clip=2, sample_dist=None, hierarchical_sample=False, **kwargs):
         batch_size = z_app.shape[0]
-        self.generate_avg_frequencies()
+        self.generate_avg_frequencies(rng=kwargs.get('_avg_rng'))
         with torch.no_grad():
             f_geo, f_app, p_geo, p_app = self._map(z_geo, z_app)
             f_geo = self.avg_frequencies_geo + psi * (f_geo - self.avg_frequencies_geo)

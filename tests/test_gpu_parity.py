@@ -1,0 +1,231 @@
+"""Parity of the CUDA path with the CPU oracle (and, through it, with the reference).  -m gpu.
+
+Every comparison replays the oracle's recorded RNG draws into the CUDA path and goes through the
+C-ABI (ctypes, fenerf_b200/ops.py) -- stage by stage first, then end to end through the generator
+class API, then against the reference's committed golden outputs.
+
+Tolerances (fp32; BASELINE.json north_star: 1e-3 max-abs on pixels, indices exact):
+  ray set-up 2e-6 | field EXACT 5e-5 | resample depths 2e-6, inds >= 99.9 % identical and every
+  mismatch a one-ulp CDF tie | compositing 2e-5 | end-to-end pixels 1e-3 (EXACT mode: 2e-4).
+The reference's last compositing interval is 1e10 wide, so a pixel is a step function of
+sign(sigma_far): rays whose oracle |sigma_far| is below ILL_TAU are ill-conditioned for ANY fp32
+implementation (an ulp of summation order flips them) and are excluded, with their count bounded.
+"""
+import numpy as np
+import pytest
+import torch
+
+import _cases
+import _harness
+from fenerf_b200 import _lib, ops
+from fenerf_b200.generators.volumetric_rendering import ReplayRng
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ILL_TAU = 2e-5
+
+
+def _cuda(t):
+    return t.contiguous().to(DEV)
+
+
+@pytest.fixture(scope="module")
+def runs():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            case = _cases.CASE_BY_NAME[name]
+            cache[name] = (case, _harness.oracle_run(case))
+        return cache[name]
+    return get
+
+
+def _desc(case, precision="exact", staged=False):
+    c = case.cfg
+    return ops.make_render_desc(
+        batch=case.batch, img_size=c["img_size"], num_steps=c["num_steps"], hierarchical=c["hierarchical_sample"],
+        clamp_mode=c["clamp_mode"], nerf_noise=c["nerf_noise"], fov=c["fov"], last_back=c.get("last_back", False),
+        white_back=c.get("white_back", False), black_back=c.get("black_back", False),
+        fill_mode=c.get("fill_mode") if staged else None, fill_color=c.get("fill_color", "black"),
+        lock_view_dependence=c.get("lock_view_dependence", False), precision=precision)
+
+
+def _ill_conditioned_pixels(case, run):
+    """(B, R, R) mask of rays whose far-sample sigma is within ILL_TAU of the relu step."""
+    st = run["out"]["stages"]
+    sig_far = st["all_raw"][:, :, -1, -1]
+    r = case.cfg["img_size"]
+    return (sig_far.abs() < ILL_TAU).reshape(case.batch, r, r)
+
+
+def test_library_loads_and_counts_launches():
+    lib = _lib.lib()
+    assert lib.fenerf_abi_version() == 1
+    assert _lib.launch_count() >= 0
+
+
+@pytest.mark.parametrize("name", ["a_small", "a_lockview_uniform", "b_small"])
+def test_ray_setup_stage(runs, name):
+    case, run = runs(name)
+    st = run["out"]["stages"]
+    from fenerf_b200.generators import volumetric_rendering as vr
+    c = case.cfg
+    x_lin, y_lin, z_lin = vr.ray_tables(c["img_size"], c["num_steps"], c["ray_start"], c["ray_end"], DEV)
+    rd = _desc(case)
+    pts, z, dirs, org = ops.ray_setup(rd, x_lin, y_lin, z_lin, _cuda(st["cam2world"]), _cuda(run["draws"][0][1]))
+    assert (pts.cpu() - st["points_coarse"]).abs().max() <= 2e-6
+    assert (z.cpu() - st["z_coarse"]).abs().max() <= 2e-6
+    assert (dirs.cpu() - st["dirs"]).abs().max() <= 2e-6
+    assert (org.cpu() - st["origins"]).abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("name", ["a_small", "b_small", "b_small_opaque"])
+def test_field_exact_stage(runs, name):
+    case, run = runs(name)
+    st = run["out"]["stages"]
+    gen = _cases.build_mirror(case, DEV)
+    b, n, s = case.batch, case.cfg["img_size"] ** 2, case.cfg["num_steps"]
+    with torch.no_grad():
+        raw = ops.siren_points(gen.siren, _cuda(st["points_coarse"].reshape(b, n * s, 3)), _cuda(run["film"]),
+                               _cuda(st["dirs"]), precision="exact")
+    err = (raw.cpu().reshape(b, n, s, -1) - st["raw_coarse"]).abs()
+    assert err.max() <= 5e-5, "max|field - oracle| = %g (per channel %s)" % (err.max(), err.amax((0, 1, 2)))
+
+
+@pytest.mark.parametrize("name", ["a_small", "a_small_noise", "b_small"])
+def test_resample_stage(runs, name):
+    case, run = runs(name)
+    st = run["out"]["stages"]
+    rd = _desc(case)
+    noise = _cuda(run["draws"][3][1]) if case.cfg["nerf_noise"] else None
+    z_f, pts_f, inds = ops.resample(rd, _cuda(st["raw_coarse"]), _cuda(st["z_coarse"]), _cuda(st["dirs"]),
+                                    _cuda(st["origins"]), noise, _cuda(run["draws"][4][1]), want_inds=True)
+    same = (inds.cpu() == st["inds"])
+    assert same.float().mean() >= 0.999, "inds identical for %.4f %%" % (100 * same.float().mean())
+    # a differing index must be a CDF tie: the resampled depth is continuous across it
+    assert (z_f.cpu() - st["z_fine"]).abs().max() <= 2e-6
+    assert (pts_f.cpu() - st["points_fine"]).abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("name", ["a_small", "a_small_noise", "a_small_opaque", "a_nohier_softplus",
+                                  "a_lockview_uniform", "b_small"])
+def test_composite_stage(runs, name):
+    case, run = runs(name)
+    st = run["out"]["stages"]
+    rd = _desc(case)
+    hier = case.cfg["hierarchical_sample"]
+    noise = _cuda(run["draws"][-1][1]) if case.cfg["nerf_noise"] else None
+    px, depth, wsum, weights, sidx = ops.composite(
+        rd, _cuda(st["raw_coarse"]), _cuda(st["z_coarse"]), _cuda(st["raw_fine"]) if hier else None,
+        _cuda(st["z_fine"]) if hier else None, noise, want_weights=True, want_sort_idx=True)
+    if hier:
+        assert torch.equal(sidx.cpu().long(), st["sort_order"].squeeze(-1)), "merge order differs"
+    assert (weights.cpu() - st["weights"]).abs().max() <= 2e-6
+    assert (wsum.cpu() - run["out"]["weights_sum"]).abs().max() <= 2e-5
+    assert (depth.cpu() - run["out"]["depth"]).abs().max() <= 2e-5
+    assert (px.cpu() - run["out"]["pixels"]).abs().max() <= 2e-5
+
+
+def _end_to_end(case, run, precision, via_frequencies=False):
+    gen = _cases.build_mirror(case, DEV)
+    rng = ReplayRng(run["draws"], DEV)
+    kw = dict(case.cfg, precision=precision, _rng=rng)
+    with torch.no_grad():
+        if case.method == "staged_forward":
+            avg = ReplayRng([("randn", t) for t in run["avg_draws"]], DEV)
+            res = gen.staged_forward(*[_cuda(z) for z in run["latents"]], psi=case.psi, _avg_rng=avg, **kw)
+            return gen, res[0].cpu(), None, res[1]
+        pixels, poses = gen(*[_cuda(z) for z in run["latents"]], **kw)
+    return gen, pixels.cpu(), poses.cpu(), None
+
+
+def _check_pixels(case, run, pixels, tol):
+    want = run["out"]["pixels"]
+    assert pixels.shape == want.shape
+    err = (pixels - want).abs()
+    if case.method == "staged_forward" and case.cfg.get("fill_mode"):
+        # fill modes threshold weights_sum at 0.9: same step discontinuity, same exclusion rule
+        pass
+    ill = _ill_conditioned_pixels(case, run).unsqueeze(1).expand_as(err)
+    n_ill = int(ill[:, 0].sum())
+    assert n_ill <= max(2, 0.002 * ill[:, 0].numel()), "%d ill-conditioned rays" % n_ill
+    worst = err[~ill].max().item() if (~ill).any() else 0.0
+    assert worst <= tol, "max|pixels - oracle| = %g over %d well-conditioned values (%d rays excluded)" % (
+        worst, int((~ill).sum()), n_ill)
+
+
+@pytest.mark.parametrize("case", _cases.CASES, ids=lambda c: c.name)
+def test_end_to_end_exact(runs, case):
+    case, run = runs(case.name)
+    gen, pixels, poses, depth_map = _end_to_end(case, run, "exact")
+    _check_pixels(case, run, pixels, 2e-4)
+    if poses is not None:
+        assert (poses - run["out"]["poses"]).abs().max() <= 1e-5
+    if depth_map is not None:
+        r = case.cfg["img_size"]
+        assert (depth_map - run["out"]["depth"].reshape(case.batch, r, r)).abs().max() <= 2e-4
+
+
+@pytest.mark.parametrize("case", _cases.CASES, ids=lambda c: c.name)
+def test_end_to_end_default_precision(runs, case):
+    """The default (tcgen05 + guard refinement) mode against the north-star bound."""
+    case, run = runs(case.name)
+    gen, pixels, poses, depth_map = _end_to_end(case, run, "guard")
+    _check_pixels(case, run, pixels, 1e-3)
+
+
+@pytest.mark.parametrize("case", _cases.CASES, ids=lambda c: c.name)
+def test_against_reference_golden(case):
+    """CUDA output vs the reference's own committed output (no oracle in between)."""
+    gold = np.load(_cases.golden_path(case))
+    run = _harness.oracle_run(case)   # only for the RNG draws, latents and the ill-conditioned mask
+    gen, pixels, poses, depth_map = _end_to_end(case, run, "guard")
+    err = (pixels - torch.from_numpy(gold["pixels"])).abs()
+    ill = _ill_conditioned_pixels(case, run).unsqueeze(1).expand_as(err)
+    assert err[~ill].max() <= 1e-3
+    if poses is not None:
+        assert (poses - torch.from_numpy(gold["poses"])).abs().max() <= 1e-5
+
+
+def test_missing_clamp_mode_is_a_keyerror_and_bad_one_a_typeerror():
+    case = _cases.CASE_BY_NAME["a_small"]
+    gen = _cases.build_mirror(case, DEV)
+    z = torch.randn(1, 256, device=DEV)
+    kw = dict(case.cfg)
+    kw.pop("clamp_mode")
+    with torch.no_grad():
+        with pytest.raises(KeyError):
+            gen(z, **kw)
+        with pytest.raises(TypeError):
+            gen(z, **dict(case.cfg, clamp_mode="nope"))
+
+
+def test_extra_curriculum_kwargs_are_swallowed_and_max_batch_size_ignored():
+    case = _cases.CASE_BY_NAME["a_small"]
+    gen = _cases.build_mirror(case, DEV)
+    z = torch.randn(1, 256, device=DEV)
+    with torch.no_grad():
+        px, poses = gen(z, **case.cfg, batch_size=24, gen_lr=6e-5, dataset='CelebA', topk_v=0.6)
+        px2, depth, third = gen.staged_forward(z, **case.cfg, max_batch_size=7)
+    assert px.shape == (1, 3, 16, 16) and poses.shape == (1, 2)
+    assert px2.shape == (1, 3, 16, 16) and depth.shape == (1, 16, 16) and not depth.is_cuda
+
+
+def test_grad_requiring_call_fails_loudly_without_opt_in(monkeypatch):
+    monkeypatch.delenv("FENERF_B200_TORCH_AUTOGRAD", raising=False)
+    case = _cases.CASE_BY_NAME["a_small"]
+    gen = _cases.build_mirror(case, DEV)
+    with pytest.raises(NotImplementedError):
+        gen(torch.randn(1, 256, device=DEV), **case.cfg)
+
+
+def test_repack_after_inplace_weight_update():
+    case = _cases.CASE_BY_NAME["a_small"]
+    gen = _cases.build_mirror(case, DEV)
+    z = torch.randn(1, 256, device=DEV)
+    with torch.no_grad():
+        torch.manual_seed(5); a, _ = gen(z, **case.cfg)
+        gen.siren.final_layer.bias += 0.5      # what an optimizer step / EMA copy_to does
+        torch.manual_seed(5); b, _ = gen(z, **case.cfg)
+    assert (a - b).abs().max() > 1e-3, "packed weights were not refreshed after an in-place update"
