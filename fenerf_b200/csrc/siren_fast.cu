@@ -1,8 +1,473 @@
-// placeholder until the tcgen05 kernel lands (replaced below in this round)
+// Point network, FAST mode: the FiLM-SIREN stack on the 5th-generation tensor cores.
+//
+// Replaces <SIREN>.forward_with_frequencies_phase_shifts (siren/siren.py:164-178, 1509-1530).
+// One persistent CTA (two per SM) walks 128-point tiles; per tile every layer is
+//     tcgen05.mma (fp16 operands, fp32 accumulator in TMEM)  ->  epilogue warps:
+//     tcgen05.ld, sin(freq * (acc + b) + phase), fp16, written back as the next layer's A operand
+// so activations never leave the SM.  Weights are pre-swizzled UMMA images in HBM/L2 (pack.cu) and
+// stream through a shared-memory ring with 1-D bulk copies (cp.async.bulk, the TMA engine).
+//
+//   warp 0       weight producer     cp.async.bulk global -> ring stage, arms full[stage]
+//   warp 1       MMA issuer          one elected lane issues tcgen05.mma / tcgen05.commit; owns TMEM
+//   warps 2..5   epilogue            one TMEM lane (= one point) per thread, 256 columns each
+//
+// The 3-wide inputs (position for the first layer, view direction for the colour layer) go through
+// the tensor cores as well, split hi/lo in fp16 on both operands (hi*hi + lo*hi + hi*lo) so they
+// keep fp32-level accuracy; grid features ride in the same 64-wide "input chunk".  The sigma / rgb
+// heads are dot products in the fp32 epilogue; the 18-way label head is one extra N=32 MMA.
+//
+// Tensor-pipe bound by design (2*256*256 FLOP per point per layer); co-limited by MUFU (one sin per
+// output element, 16/clk/SM) and by the L2->SM weight stream (128 KB per layer per 128-point tile).
+//
+// Shared memory (<= 113 KB so two CTAs share an SM; TMEM 256 columns each):
+//   A     4 x 16 KB   activations [128 rows][64 k] f16 x 4 k-chunks, 128B swizzle, K-major
+//   X     16 KB       input chunk [128 rows][64 slots]   (layout.h: slot order)
+//   ring  2 x 16 KB   weight stages [128 n-rows][64 k] (half of one k-chunk image)
 #include "common.cuh"
+#include "siren_common.cuh"
+
 namespace fn {
-int siren_points_fast(const FnLayout&, const unsigned char*, const float*, const float*, const float*, int, long long,
-                      int, int, float*, cudaStream_t) {
-    return fail(FENERF_E_UNSUPPORTED, "tcgen05 point-network kernel not built");
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int NTHREADS = 192;
+constexpr int RING = 2;
+constexpr uint32_t STAGE_BYTES = 16384;
+constexpr uint32_t A_CHUNK_BYTES = 16384;
+constexpr uint32_t SMEM_A = 0;
+constexpr uint32_t SMEM_X = 4 * A_CHUNK_BYTES;
+constexpr uint32_t SMEM_RING = SMEM_X + A_CHUNK_BYTES;
+constexpr uint32_t SMEM_BAR = SMEM_RING + RING * STAGE_BYTES;   // 114688
+constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 128;
+constexpr int TMEM_COLS = 256;
+constexpr int MAX_LOADS = 96;
+constexpr int MAX_STAGES = 16;
+
+enum : uint8_t { EPI_FILM = 0, EPI_FILM_SIGMA = 1, EPI_LABEL = 2, EPI_FILM_RGB = 3 };
+
+struct LoadOp {            // one ring stage: a bulk copy and the MMAs that consume it
+    uint32_t src;          // byte offset in the packed buffer
+    uint16_t bytes;        // multiple of 16, <= STAGE_BYTES (stored / 16)
+    uint8_t a_chunk;       // 0..3 activation chunk, 4 = input chunk
+    uint8_t k0, nk;        // K-steps (16 wide) inside the 64-wide chunk
+    uint8_t n8;            // MMA N / 8
+    uint16_t d_col;        // accumulator column offset
+    uint8_t first;         // 1: first MMA of this accumulator range (overwrite instead of accumulate)
+    uint8_t last;          // 1: last load of its stage -> commit the accumulator
+    uint8_t pad[2];
+};
+
+struct StageOp {
+    uint8_t epi;           // EPI_*
+    uint8_t film;          // FiLM layer index
+    uint8_t n_loads;
+    uint8_t pad;
+};
+
+struct FastArgs {
+    LoadOp loads[MAX_LOADS];
+    StageOp stages[MAX_STAGES];
+    int n_loads, n_stages;
+    FnLayout L;
+    const unsigned char* packed;
+    const float* points;
+    const float* dirs;
+    const float* film;
+    float* out;
+    long long ppb, tiles_per_batch, n_tiles;
+    int dir_group, lock_dirs;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO),
+// LBO unused for swizzled K-major, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+// instruction descriptor, kind::f16: D f32, A/B f16, both K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
+    return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_constant__ FastArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + SMEM_BAR;            // RING x 8 B
+    const uint32_t bar_empty = bar_full + 8 * RING;        // RING x 8 B
+    const uint32_t bar_acc = bar_empty + 8 * RING;         // accumulator ready (MMA -> epilogue)
+    const uint32_t bar_aready = bar_acc + 8;               // A operand ready + TMEM drained (epilogue -> MMA)
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * RING + 2));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        mbar_init(bar_acc, 1);
+        mbar_init(bar_aready, 4);      // one arrival per epilogue warp
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const FnLayout& L = a.L;
+
+    if (warp == 0) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int i = 0; i < a.n_loads; ++i, ++it) {
+                    const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                    mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+                    const uint32_t bytes = (uint32_t)a.loads[i].bytes * 16u;
+                    mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+                    bulk_g2s(sbase + SMEM_RING + slot * STAGE_BYTES, a.packed + a.loads[i].src, bytes, bar_full + 8 * slot);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, n_ready = 0;
+            for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                int li = 0;
+                for (int s = 0; s < a.n_stages; ++s) {
+                    mbar_wait(bar_aready, n_ready & 1);     // inputs written, accumulator drained
+                    ++n_ready;
+                    tc_fence_after();
+                    for (int j = 0; j < a.stages[s].n_loads; ++j, ++li, ++it) {
+                        const LoadOp op = a.loads[li];
+                        const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                        mbar_wait(bar_full + 8 * slot, ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = sbase + (op.a_chunk < 4 ? SMEM_A + op.a_chunk * A_CHUNK_BYTES : SMEM_X);
+                        const uint32_t b_addr = sbase + SMEM_RING + slot * STAGE_BYTES;
+                        const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u);
+                        for (int k = 0; k < op.nk; ++k) {
+                            const uint32_t koff = (uint32_t)(op.k0 + k) * 32u;      // 16 f16 = 32 B inside the swizzle row
+                            tc_mma_f16(tmem_base + op.d_col, umma_desc_sw128(a_addr + koff), umma_desc_sw128(b_addr + koff),
+                                       idesc, (op.first && k == 0) ? 0u : 1u);
+                        }
+                        tc_commit(bar_empty + 8 * slot);      // ring stage reusable once these MMAs retire
+                        if (op.last) tc_commit(bar_acc);      // accumulator complete for this stage
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;                // point slot in the tile
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+        const uint32_t sw = (uint32_t)(row & 7);
+        const int C = L.out_dim;
+        const float* sigma_w = reinterpret_cast<const float*>(a.packed + L.sigma_w);
+        const float* rgb_w = reinterpret_cast<const float*>(a.packed + L.rgb_w);
+        const float* label_w = reinterpret_cast<const float*>(a.packed + L.label_w);
+        uint32_t n_acc = 0;
+        for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            // ---- build the input chunk for this tile ----
+            const long long b = tile / a.tiles_per_batch;
+            const long long p = (tile % a.tiles_per_batch) * TILE + row;
+            const bool valid = p < a.ppb;
+            const long long flat = b * a.ppb + p;
+            {
+                float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) pos[i] = __fmul_rn(a.points[flat * 3 + i], L.input_scale);
+                    if (a.lock_dirs) dir[2] = -1.f;
+                    else {
+                        const long long di = b * (a.ppb / a.dir_group) + p / a.dir_group;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) dir[i] = a.dirs[di * 3 + i];
+                    }
+                }
+                __align__(16) __half slots[64];
+#pragma unroll
+                for (int i = 0; i < 64; ++i) slots[i] = __float2half_rn(0.f);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    __half hi, lo;
+                    split_f16(pos[i], hi, lo);
+                    slots[FN_SLOT_POS + i] = hi; slots[FN_SLOT_POS + 3 + i] = lo; slots[FN_SLOT_POS + 6 + i] = hi;
+                    split_f16(dir[i], hi, lo);
+                    slots[FN_SLOT_DIR + i] = hi; slots[FN_SLOT_DIR + 3 + i] = lo; slots[FN_SLOT_DIR + 6 + i] = hi;
+                }
+                if (L.grid_channels > 0 && valid) {
+                    float feat[32];
+                    grid_features32(reinterpret_cast<const float*>(a.packed + L.grid), L.grid_res, pos[0], pos[1], pos[2], feat);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) slots[FN_SLOT_FEAT + i] = __float2half_rn(feat[i]);
+                }
+                const uint4* src = reinterpret_cast<const uint4*>(slots);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(smem + SMEM_X + row_off + (((uint32_t)j ^ sw) << 4)) = src[j];
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_aready);
+
+            float sigma = 0.f;
+            for (int s = 0; s < a.n_stages; ++s) {
+                const StageOp sop = a.stages[s];
+                mbar_wait(bar_acc, n_acc & 1);
+                ++n_acc;
+                tc_fence_after();
+                if (sop.epi == EPI_LABEL) {
+                    uint32_t r[32];
+                    tc_ld32(t_lane, r);
+                    tc_wait_ld();
+                    if (valid) {
+                        const float inv_scale = __ldg(label_w + FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL);
+                        for (int o = 0; o < L.label_dim; ++o)
+                            a.out[flat * C + o] = fmaf(__uint_as_float(r[o]), inv_scale, __ldg(label_w + FENERF_MAX_LABEL * FN_H + o));
+                    }
+                } else {
+                    const float* fl = a.film + ((size_t)b * L.n_film + sop.film) * 2 * FN_H;
+                    const float* bias = reinterpret_cast<const float*>(
+                        a.packed + (sop.film == 0 ? L.first_b : L.hid_b[sop.film - 1]));
+                    float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+                    if (sop.epi == EPI_FILM_SIGMA) sigma = __ldg(sigma_w + FN_H);
+                    if (sop.epi == EPI_FILM_RGB) { rgb0 = __ldg(rgb_w + 3 * FN_H); rgb1 = __ldg(rgb_w + 3 * FN_H + 1); rgb2 = __ldg(rgb_w + 3 * FN_H + 2); }
+#pragma unroll 1
+                    for (int g = 0; g < 8; ++g) {         // 8 groups of 32 accumulator columns
+                        uint32_t r[32];
+                        tc_ld32(t_lane + g * 32, r);
+                        tc_wait_ld();
+                        float v[32];
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const int c = g * 32 + j4 * 4;
+                            const float4 fr = __ldg(reinterpret_cast<const float4*>(fl + c));
+                            const float4 ph = __ldg(reinterpret_cast<const float4*>(fl + FN_H + c));
+                            const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c));
+                            v[j4 * 4 + 0] = __sinf(fmaf(fr.x, __uint_as_float(r[j4 * 4 + 0]) + bs.x, ph.x));
+                            v[j4 * 4 + 1] = __sinf(fmaf(fr.y, __uint_as_float(r[j4 * 4 + 1]) + bs.y, ph.y));
+                            v[j4 * 4 + 2] = __sinf(fmaf(fr.z, __uint_as_float(r[j4 * 4 + 2]) + bs.z, ph.z));
+                            v[j4 * 4 + 3] = __sinf(fmaf(fr.w, __uint_as_float(r[j4 * 4 + 3]) + bs.w, ph.w));
+                        }
+                        if (sop.epi == EPI_FILM_SIGMA) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sigma = fmaf(v[j], __ldg(sigma_w + g * 32 + j), sigma);
+                        }
+                        if (sop.epi == EPI_FILM_RGB) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                rgb0 = fmaf(v[j], __ldg(rgb_w + g * 32 + j), rgb0);
+                                rgb1 = fmaf(v[j], __ldg(rgb_w + FN_H + g * 32 + j), rgb1);
+                                rgb2 = fmaf(v[j], __ldg(rgb_w + 2 * FN_H + g * 32 + j), rgb2);
+                            }
+                        } else {
+                            // 32 columns = half of k-chunk (g / 2): four 16-byte pieces, swizzled
+                            unsigned char* chunk = smem + SMEM_A + (uint32_t)(g >> 1) * A_CHUNK_BYTES + row_off;
+#pragma unroll
+                            for (int j8 = 0; j8 < 4; ++j8) {
+                                uint4 pk;
+                                pk.x = pack_half2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+                                pk.y = pack_half2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                                pk.z = pack_half2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+                                pk.w = pack_half2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+                                const uint32_t piece = (uint32_t)((g & 1) * 4 + j8);
+                                *reinterpret_cast<uint4*>(chunk + ((piece ^ sw) << 4)) = pk;
+                            }
+                        }
+                    }
+                    if (sop.epi == EPI_FILM_SIGMA && valid) a.out[flat * C + (C - 1)] = sigma;
+                    if (sop.epi == EPI_FILM_RGB && valid) {
+                        a.out[flat * C + L.label_dim + 0] = __fdividef(1.f, 1.f + __expf(-rgb0));
+                        a.out[flat * C + L.label_dim + 1] = __fdividef(1.f, 1.f + __expf(-rgb1));
+                        a.out[flat * C + L.label_dim + 2] = __fdividef(1.f, 1.f + __expf(-rgb2));
+                    }
+                }
+                if (s + 1 < a.n_stages) {
+                    // next stage may overwrite the accumulator and read what was just written
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_aready);
+                }
+            }
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host: the per-tile stage / load program --------------------------------------------------
+struct Program {
+    FastArgs args;
+    bool ok;
+};
+
+void push_image_loads(FastArgs& A, size_t img_off, int a_chunk0, int n_chunks, bool first_of_stage) {
+    // a [256][64] image per k-chunk, loaded as two 128-row halves
+    for (int kc = 0; kc < n_chunks; ++kc)
+        for (int half = 0; half < 2; ++half) {
+            LoadOp& op = A.loads[A.n_loads++];
+            op.src = (uint32_t)(img_off + (size_t)kc * FN_IMG_BYTES + (size_t)half * STAGE_BYTES);
+            op.bytes = STAGE_BYTES / 16;
+            op.a_chunk = (uint8_t)(a_chunk0 + kc);
+            op.k0 = 0; op.nk = 4; op.n8 = 128 / 8; op.d_col = (uint16_t)(half * 128);
+            op.first = (first_of_stage && kc == 0) ? 1 : 0;
+            op.last = 0;
+        }
+}
+
+bool build_program(const FnLayout& L, FastArgs& A) {
+    A.n_loads = 0; A.n_stages = 0;
+    auto end_stage = [&](uint8_t epi, uint8_t film, int first_load) {
+        StageOp& st = A.stages[A.n_stages++];
+        st.epi = epi; st.film = film; st.n_loads = (uint8_t)(A.n_loads - first_load); st.pad = 0;
+        A.loads[A.n_loads - 1].last = 1;
+    };
+    // first layer: only K-step 0 of the input chunk (position hi/lo slots)
+    {
+        int l0 = A.n_loads;
+        for (int half = 0; half < 2; ++half) {
+            LoadOp& op = A.loads[A.n_loads++];
+            op.src = (uint32_t)(L.first_img + (size_t)half * STAGE_BYTES);
+            op.bytes = STAGE_BYTES / 16; op.a_chunk = 4; op.k0 = 0; op.nk = 1; op.n8 = 16; op.d_col = (uint16_t)(half * 128);
+            op.first = 1; op.last = 0;
+        }
+        end_stage(EPI_FILM, 0, l0);
+    }
+    for (int l = 0; l < L.n_hidden; ++l) {
+        if (l == L.trunk_hidden && L.label_dim > 0) {
+            int l0 = A.n_loads;
+            for (int kc = 0; kc < 4; ++kc) {
+                LoadOp& op = A.loads[A.n_loads++];
+                op.src = (uint32_t)(L.label_img + (size_t)kc * (32 * FN_KCHUNK * 2));
+                op.bytes = (32 * FN_KCHUNK * 2) / 16; op.a_chunk = (uint8_t)kc; op.k0 = 0; op.nk = 4; op.n8 = 32 / 8; op.d_col = 0;
+                op.first = kc == 0; op.last = 0;
+            }
+            end_stage(EPI_LABEL, 0, l0);
+        }
+        int l0 = A.n_loads;
+        push_image_loads(A, L.hid_img[l], 0, 4, true);
+        if (l == L.trunk_hidden) {
+            // extra inputs of the first colour layer: K-steps 1.. of the input chunk (dir, then grid features)
+            const int nk = L.grid_channels > 0 ? 3 : 1;
+            for (int half = 0; half < 2; ++half) {
+                LoadOp& op = A.loads[A.n_loads++];
+                op.src = (uint32_t)(L.color0_ximg + (size_t)half * STAGE_BYTES);
+                op.bytes = STAGE_BYTES / 16; op.a_chunk = 4; op.k0 = 1; op.nk = (uint8_t)nk; op.n8 = 16; op.d_col = (uint16_t)(half * 128);
+                op.first = 0; op.last = 0;
+            }
+        }
+        uint8_t epi = EPI_FILM;
+        if (l == L.trunk_hidden - 1) epi = EPI_FILM_SIGMA;
+        if (l == L.n_hidden - 1) epi = EPI_FILM_RGB;
+        end_stage(epi, (uint8_t)(l + 1), l0);
+        if (A.n_loads > MAX_LOADS - 12 || A.n_stages > MAX_STAGES - 2) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+int siren_points_fast(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
+                      const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
+                      cudaStream_t st) {
+    static_assert(sizeof(FastArgs) <= 4000, "kernel parameter block too large");
+    static_assert(SMEM_TOTAL <= 115712, "two CTAs per SM must fit");
+    FN_REQUIRE(L.trunk_hidden >= 1 && L.n_hidden - L.trunk_hidden >= 1, "field needs >= 2 trunk and >= 1 colour layers");
+    FN_REQUIRE(L.trunk_hidden - 1 != L.n_hidden - 1, "internal: sigma and rgb epilogues coincide");
+    FastArgs a;
+    memset(&a, 0, sizeof(a));
+    FN_REQUIRE(build_program(L, a), "field too deep for the stage program");
+    a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out;
+    a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
+    a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs;
+    if (a.n_tiles <= 0) return 0;
+    FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);
+    FN_CUDA_OK(cudaFuncSetAttribute(siren_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    int blocks = (int)(a.n_tiles < (long long)num_sms() * 2 ? a.n_tiles : (long long)num_sms() * 2);
+    siren_fast_kernel<<<blocks, NTHREADS, SMEM_TOTAL, st>>>(a);
+    FN_LAUNCH_OK("siren_fast_kernel");
+    return 0;
+}
+
 }  // namespace fn
