@@ -41,7 +41,7 @@ constexpr uint32_t SMEM_RING = SMEM_X + A_CHUNK_BYTES;
 constexpr uint32_t SMEM_BAR = SMEM_RING + RING * STAGE_BYTES;   // 114688
 constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 128;
 constexpr int TMEM_COLS = 256;
-constexpr int MAX_LOADS = 96;
+constexpr int MAX_LOADS = 128;
 constexpr int MAX_STAGES = 16;
 
 enum : uint8_t { EPI_FILM = 0, EPI_FILM_SIGMA = 1, EPI_LABEL = 2, EPI_FILM_RGB = 3 };
