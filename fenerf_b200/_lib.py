@@ -22,7 +22,7 @@ E_CLAMP_MODE = -5
 EXPORTS = (
     "fenerf_packed_bytes", "fenerf_pack_field", "fenerf_siren_points", "fenerf_ray_setup", "fenerf_resample",
     "fenerf_composite", "fenerf_workspace_bytes", "fenerf_render_forward", "fenerf_last_error",
-    "fenerf_abi_version", "fenerf_launch_count",
+    "fenerf_abi_version", "fenerf_launch_count", "fenerf_debug_trace",
 )
 
 
@@ -78,6 +78,8 @@ def _declare(lib):
     lib.fenerf_abi_version.argtypes = []
     lib.fenerf_launch_count.restype = i64
     lib.fenerf_launch_count.argtypes = []
+    lib.fenerf_debug_trace.restype = None
+    lib.fenerf_debug_trace.argtypes = [vp]
 
 
 def lib():

@@ -64,6 +64,7 @@ extern "C" {
 
 const char* fenerf_last_error(void) { return g_err; }
 int32_t fenerf_abi_version(void) { return FENERF_ABI_VERSION; }
+void fenerf_debug_trace(void* device_buffer) { set_fast_trace(static_cast<long long*>(device_buffer)); }
 int64_t fenerf_launch_count(void) { return (int64_t)g_launches.load(); }
 
 size_t fenerf_packed_bytes(const fenerf_field_desc* field) {

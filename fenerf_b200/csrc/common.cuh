@@ -66,6 +66,7 @@ int siren_points_exact(const FnLayout& L, const unsigned char* packed, const flo
 int siren_points_fast(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
                       cudaStream_t st);
+void set_fast_trace(long long* buf);
 int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                  const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
                  float* raw, int32_t* scratch_idx, cudaStream_t st);

@@ -13,7 +13,9 @@
 //        f16:  one more 64-wide chunk in the "input chunk" slot order (see below)
 //   input-chunk image of the first layer: [256 rows][64 k] f16 (only slots 0..8 non-zero)
 //   heads            sigma: w[256], b[1]   rgb: w[3][256], b[3]   label: Weff[L][256], beff[L] (f32)
-//                    label image [4 chunks][32 rows][64 k] f16 swizzled (rows >= L zero)
+//                    trunk-head image [4 chunks][32 rows][64 k] f16 swizzled: rows 0..L-1 the
+//                    (power-of-two scaled) label map, row L the sigma weights, rest zero
+//                    rgb-head image   [4 chunks][ 8 rows][64 k] f16 swizzled: rows 0..2
 //   grid             channels-last [R][R][R][G] f32
 //
 // "Input chunk" slot order (the 64-wide A chunk the tcgen05 kernel builds per point):
@@ -44,7 +46,7 @@ struct FnLayout {
     size_t first_w, first_b, first_img;
     size_t hid_w32[FN_MAX_HIDDEN], hid_b[FN_MAX_HIDDEN], hid_img[FN_MAX_HIDDEN];
     size_t color0_ximg;     // input-chunk image of the first colour layer
-    size_t sigma_w, rgb_w, label_w, label_img, label_scratch;
+    size_t sigma_w, rgb_w, label_w, head_img, rgb_img, label_scratch;
     size_t grid;
     size_t total;
 };
@@ -86,7 +88,8 @@ static inline int fn_make_layout(const fenerf_field_desc* f, FnLayout* L) {
     L->sigma_w = take((FN_H + 1) * 4);
     L->rgb_w = take((3 * FN_H + 3) * 4);
     L->label_w = take((size_t)(FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL + 1) * 4);  // Weff, beff, 1/scale
-    L->label_img = take((size_t)(FN_H / FN_KCHUNK) * 32 * FN_KCHUNK * 2);
+    L->head_img = take((size_t)(FN_H / FN_KCHUNK) * 32 * FN_KCHUNK * 2);
+    L->rgb_img = take((size_t)(FN_H / FN_KCHUNK) * 8 * FN_KCHUNK * 2);
     L->label_scratch = take((size_t)FENERF_MAX_LABEL * (FN_H + 1) * 8);  // doubles, pack-time only
     size_t r = (size_t)f->grid_res;
     L->grid = take(f->grid_channels ? r * r * r * (size_t)f->grid_channels * 4 : 4);

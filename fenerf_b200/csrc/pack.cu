@@ -116,9 +116,9 @@ __global__ void label_step2_kernel(const double* __restrict__ u, const float* __
     }
 }
 // step 3 (one block): power-of-two scale so that max|Weff| lands in [0.25, 0.5) -- random-init
-// products of three 1/25-scaled layers sit in the fp16 subnormal range otherwise -- then the
-// swizzled f16 image; 1/scale is stored after the biases for the epilogue.
-__global__ void label_step3_kernel(float* __restrict__ lw, int L, unsigned char* __restrict__ img) {
+// products of three 1/25-scaled layers sit in the fp16 subnormal range otherwise; 1/scale is stored
+// after the biases for the epilogue.
+__global__ void label_step3_kernel(float* __restrict__ lw, int L) {
     __shared__ float smax[256];
     float m = 0.f;
     for (int i = threadIdx.x; i < L * FN_H; i += blockDim.x) m = fmaxf(m, fabsf(lw[i]));
@@ -134,10 +134,27 @@ __global__ void label_step3_kernel(float* __restrict__ lw, int L, unsigned char*
     float scale = ldexpf(1.f, -e - 1);                    // mx * scale in [0.25, 0.5)
     if (!(mx > 0.f)) scale = 1.f;
     if (threadIdx.x == 0) lw[FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL] = 1.f / scale;
+}
+
+// head images for the tcgen05 kernel (one block):
+//   trunk head  [4][32 rows][64 k]: rows 0..L-1 = Weff * scale, row L = sigma weights
+//   rgb head    [4][ 8 rows][64 k]: rows 0..2
+__global__ void pack_head_imgs_kernel(const float* __restrict__ lw, int L, const float* __restrict__ sigma_w,
+                                      const float* __restrict__ rgb_w, unsigned char* __restrict__ head_img,
+                                      unsigned char* __restrict__ rgb_img) {
+    const float scale = L > 0 ? 1.f / lw[FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL] : 1.f;
     for (int i = threadIdx.x; i < 32 * FN_H; i += blockDim.x) {
         int row = i / FN_H, k = i % FN_H;
-        float v = row < L ? lw[row * FN_H + k] * scale : 0.f;
-        unsigned char* chunk = img + (size_t)(k / FN_KCHUNK) * (32 * FN_KCHUNK * 2);
+        float v = 0.f;
+        if (row < L) v = lw[row * FN_H + k] * scale;
+        else if (row == L) v = sigma_w[k];
+        unsigned char* chunk = head_img + (size_t)(k / FN_KCHUNK) * (32 * FN_KCHUNK * 2);
+        *reinterpret_cast<__half*>(chunk + fn_sw128_offset(row, k % FN_KCHUNK)) = __float2half_rn(v);
+    }
+    for (int i = threadIdx.x; i < 8 * FN_H; i += blockDim.x) {
+        int row = i / FN_H, k = i % FN_H;
+        float v = row < 3 ? rgb_w[row * FN_H + k] : 0.f;
+        unsigned char* chunk = rgb_img + (size_t)(k / FN_KCHUNK) * (8 * FN_KCHUNK * 2);
         *reinterpret_cast<__half*>(chunk + fn_sw128_offset(row, k % FN_KCHUNK)) = __float2half_rn(v);
     }
 }
@@ -198,9 +215,12 @@ int pack_field(const fenerf_field_desc* f, const FnLayout& L, const fenerf_field
         label_step2_kernel<<<L.label_dim, FN_H, 0, st>>>(u, p->label_w[0], p->label_b[0], L.label_dim,
                                                          (float*)(packed + L.label_w));
         FN_LAUNCH_OK("label_step2_kernel");
-        label_step3_kernel<<<1, 256, 0, st>>>((float*)(packed + L.label_w), L.label_dim, packed + L.label_img);
+        label_step3_kernel<<<1, 256, 0, st>>>((float*)(packed + L.label_w), L.label_dim);
         FN_LAUNCH_OK("label_step3_kernel");
     }
+    pack_head_imgs_kernel<<<1, 256, 0, st>>>((const float*)(packed + L.label_w), L.label_dim, p->sigma_w, p->rgb_w,
+                                             packed + L.head_img, packed + L.rgb_img);
+    FN_LAUNCH_OK("pack_head_imgs_kernel");
     if (L.grid_channels > 0) {
         FN_REQUIRE(p->grid, "grid missing");
         int R = L.grid_res, G = L.grid_channels;

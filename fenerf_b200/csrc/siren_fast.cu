@@ -1,28 +1,37 @@
 // Point network, FAST mode: the FiLM-SIREN stack on the 5th-generation tensor cores.
 //
 // Replaces <SIREN>.forward_with_frequencies_phase_shifts (siren/siren.py:164-178, 1509-1530).
-// One persistent CTA (two per SM) walks 128-point tiles; per tile every layer is
+// One persistent CTA (two per SM) walks 128-point tiles; per tile every FiLM layer is
 //     tcgen05.mma (fp16 operands, fp32 accumulator in TMEM)  ->  epilogue warps:
-//     tcgen05.ld, sin(freq * (acc + b) + phase), fp16, written back as the next layer's A operand
+//     tcgen05.ld, sin(freq * (acc + b) + phase), fp16, written back as the next layer's operand
 // so activations never leave the SM.  Weights are pre-swizzled UMMA images in HBM/L2 (pack.cu) and
 // stream through a shared-memory ring with 1-D bulk copies (cp.async.bulk, the TMA engine).
 //
 //   warp 0       weight producer     cp.async.bulk global -> ring stage, arms full[stage]
 //   warp 1       MMA issuer          one elected lane issues tcgen05.mma / tcgen05.commit; owns TMEM
-//   warps 2..5   epilogue            one TMEM lane (= one point) per thread, 256 columns each
+//   warps 2..5   epilogue            128 threads
+//
+// Orientation.  The FiLM layers run TRANSPOSED: D^T[feature][point] = W[feature][k] . X[point][k],
+// i.e. the weight image is the MMA's A operand (M = 128 features per half) and the activation tile
+// its B operand (N = 128 points).  An epilogue thread then owns one TMEM lane = one output feature:
+// its FiLM constants (freq, freq*bias + phase) sit in two registers, each of its 2 x 128 accumulator
+// values costs FFMA + FMUL + MUFU.SIN + F2FP + a 2-byte shared store, and nothing is re-loaded per
+// column (the first version of this kernel had points on lanes and spent ~5x the MUFU-bound time
+// waiting on per-column FiLM loads; profiles/r01_trace_v1.txt).  The activation tile is K-major
+// [point][k] in both roles, so the small heads run in the other orientation on the same buffer:
+// D[point][head] with the tile as A (M = 128 points) and an 8- or 32-row head image as B.
 //
 // The 3-wide inputs (position for the first layer, view direction for the colour layer) go through
 // the tensor cores as well, split hi/lo in fp16 on both operands (hi*hi + lo*hi + hi*lo) so they
-// keep fp32-level accuracy; grid features ride in the same 64-wide "input chunk".  The sigma / rgb
-// heads are dot products in the fp32 epilogue; the 18-way label head is one extra N=32 MMA.
+// keep fp32-level accuracy; grid features ride in the same 64-wide "input chunk".
 //
 // Tensor-pipe bound by design (2*256*256 FLOP per point per layer); co-limited by MUFU (one sin per
 // output element, 16/clk/SM) and by the L2->SM weight stream (128 KB per layer per 128-point tile).
 //
 // Shared memory (<= 113 KB so two CTAs share an SM; TMEM 256 columns each):
-//   A     4 x 16 KB   activations [128 rows][64 k] f16 x 4 k-chunks, 128B swizzle, K-major
-//   X     16 KB       input chunk [128 rows][64 slots]   (layout.h: slot order)
-//   ring  2 x 16 KB   weight stages [128 n-rows][64 k] (half of one k-chunk image)
+//   A     4 x 16 KB   activations [128 points][64 k] f16 x 4 k-chunks, 128B swizzle, K-major
+//   X     16 KB       input chunk [128 points][64 slots]   (layout.h: slot order)
+//   ring  2 x 16 KB   weight stages [128 feature rows][64 k] (half of one k-chunk image)
 #include "common.cuh"
 #include "siren_common.cuh"
 
@@ -44,18 +53,19 @@ constexpr int TMEM_COLS = 256;
 constexpr int MAX_LOADS = 128;
 constexpr int MAX_STAGES = 16;
 
-enum : uint8_t { EPI_FILM = 0, EPI_FILM_SIGMA = 1, EPI_LABEL = 2, EPI_FILM_RGB = 3 };
+enum : uint8_t { EPI_FILM = 0, EPI_HEAD_TRUNK = 1, EPI_HEAD_RGB = 2 };
 
 struct LoadOp {            // one ring stage: a bulk copy and the MMAs that consume it
     uint32_t src;          // byte offset in the packed buffer
     uint16_t bytes;        // multiple of 16, <= STAGE_BYTES (stored / 16)
-    uint8_t a_chunk;       // 0..3 activation chunk, 4 = input chunk
+    uint8_t a_chunk;       // activation chunk 0..3, 4 = input chunk
     uint8_t k0, nk;        // K-steps (16 wide) inside the 64-wide chunk
     uint8_t n8;            // MMA N / 8
     uint16_t d_col;        // accumulator column offset
     uint8_t first;         // 1: first MMA of this accumulator range (overwrite instead of accumulate)
     uint8_t last;          // 1: last load of its stage -> commit the accumulator
-    uint8_t pad[2];
+    uint8_t w_is_a;        // 1: ring stage is the A operand (transposed FiLM layer); 0: it is B (head)
+    uint8_t pad;
 };
 
 struct StageOp {
@@ -77,6 +87,7 @@ struct FastArgs {
     float* out;
     long long ppb, tiles_per_batch, n_tiles;
     int dir_group, lock_dirs;
+    long long* trace;   // diagnostics: per-role clock64 log of CTA 0 (fenerf_debug_trace), or NULL
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -131,6 +142,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO),
@@ -156,6 +172,15 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn(v - __half2float(hi));
 }
+
+// Diagnostics: CTA 0 logs (tag, clock64) pairs for its first tiles; one 4096-entry lane per role.
+struct Tracer {
+    long long* p; int n;
+    __device__ Tracer(long long* base, int role) : p(base && blockIdx.x == 0 ? base + role * 4096 : nullptr), n(0) {}
+    __device__ __forceinline__ void log(int kind, int tile, int stage, int item) {
+        if (p && tile < 2 && n < 2040) { p[2 + 2 * n] = ((long long)kind << 48) | ((long long)tile << 32) | (stage << 16) | item; p[3 + 2 * n] = clock64(); ++n; p[0] = n; }
+    }
+};
 
 // ---- the kernel -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_constant__ FastArgs a) {
@@ -189,10 +214,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            Tracer tr(a.trace, 0);
+            int tl = 0;
+            for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
                 for (int i = 0; i < a.n_loads; ++i, ++it) {
                     const uint32_t slot = it % RING, ph = (it / RING) & 1;
                     mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+                    tr.log('E', tl, 0, i);
                     const uint32_t bytes = (uint32_t)a.loads[i].bytes * 16u;
                     mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
                     bulk_g2s(sbase + SMEM_RING + slot * STAGE_BYTES, a.packed + a.loads[i].src, bytes, bar_full + 8 * slot);
@@ -203,19 +231,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t it = 0, n_ready = 0;
-            for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            Tracer tr(a.trace, 1);
+            int tl = 0;
+            for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
                 int li = 0;
                 for (int s = 0; s < a.n_stages; ++s) {
                     mbar_wait(bar_aready, n_ready & 1);     // inputs written, accumulator drained
                     ++n_ready;
                     tc_fence_after();
+                    tr.log('A', tl, s, 0);
                     for (int j = 0; j < a.stages[s].n_loads; ++j, ++li, ++it) {
                         const LoadOp op = a.loads[li];
                         const uint32_t slot = it % RING, ph = (it / RING) & 1;
                         mbar_wait(bar_full + 8 * slot, ph);
                         tc_fence_after();
-                        const uint32_t a_addr = sbase + (op.a_chunk < 4 ? SMEM_A + op.a_chunk * A_CHUNK_BYTES : SMEM_X);
-                        const uint32_t b_addr = sbase + SMEM_RING + slot * STAGE_BYTES;
+                        tr.log('F', tl, s, li);
+                        const uint32_t x_addr = sbase + (op.a_chunk < 4 ? SMEM_A + op.a_chunk * A_CHUNK_BYTES : SMEM_X);
+                        const uint32_t w_addr = sbase + SMEM_RING + slot * STAGE_BYTES;
+                        const uint32_t a_addr = op.w_is_a ? w_addr : x_addr;
+                        const uint32_t b_addr = op.w_is_a ? x_addr : w_addr;
                         const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u);
                         for (int k = 0; k < op.nk; ++k) {
                             const uint32_t koff = (uint32_t)(op.k0 + k) * 32u;      // 16 f16 = 32 B inside the swizzle row
@@ -223,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
                                        idesc, (op.first && k == 0) ? 0u : 1u);
                         }
                         tc_commit(bar_empty + 8 * slot);      // ring stage reusable once these MMAs retire
-                        if (op.last) tc_commit(bar_acc);      // accumulator complete for this stage
+                        if (op.last) { tc_commit(bar_acc); tr.log('C', tl, s, li); }   // accumulator complete for this stage
                     }
                 }
             }
@@ -240,7 +274,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
         const float* rgb_w = reinterpret_cast<const float*>(a.packed + L.rgb_w);
         const float* label_w = reinterpret_cast<const float*>(a.packed + L.label_w);
         uint32_t n_acc = 0;
-        for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        Tracer tr(warp == 2 && lane == 0 ? a.trace : nullptr, 2);
+        int tl = 0;
+        for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
+            tr.log('T', tl, 0, 0);
             // ---- build the input chunk for this tile ----
             const long long b = tile / a.tiles_per_batch;
             const long long p = (tile % a.tiles_per_batch) * TILE + row;
@@ -285,78 +322,88 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_aready);
 
-            float sigma = 0.f;
             for (int s = 0; s < a.n_stages; ++s) {
                 const StageOp sop = a.stages[s];
-                mbar_wait(bar_acc, n_acc & 1);
-                ++n_acc;
-                tc_fence_after();
-                if (sop.epi == EPI_LABEL) {
-                    uint32_t r[32];
-                    tc_ld32(t_lane, r);
-                    tc_wait_ld();
-                    if (valid) {
-                        const float inv_scale = __ldg(label_w + FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL);
-                        for (int o = 0; o < L.label_dim; ++o)
-                            a.out[flat * C + o] = fmaf(__uint_as_float(r[o]), inv_scale, __ldg(label_w + FENERF_MAX_LABEL * FN_H + o));
-                    }
-                } else {
-                    const float* fl = a.film + ((size_t)b * L.n_film + sop.film) * 2 * FN_H;
+                if (sop.epi == EPI_FILM) {
+                    // this thread's two output features: fl and 128 + fl (one per accumulator half);
+                    // FiLM constants fetched before the accumulator wait so their latency is hidden
+                    const int fl = row;
+                    const float* film_l = a.film + ((size_t)b * L.n_film + sop.film) * 2 * FN_H;
                     const float* bias = reinterpret_cast<const float*>(
                         a.packed + (sop.film == 0 ? L.first_b : L.hid_b[sop.film - 1]));
-                    float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-                    if (sop.epi == EPI_FILM_SIGMA) sigma = __ldg(sigma_w + FN_H);
-                    if (sop.epi == EPI_FILM_RGB) { rgb0 = __ldg(rgb_w + 3 * FN_H); rgb1 = __ldg(rgb_w + 3 * FN_H + 1); rgb2 = __ldg(rgb_w + 3 * FN_H + 2); }
-#pragma unroll 1
-                    for (int g = 0; g < 8; ++g) {         // 8 groups of 32 accumulator columns
-                        uint32_t r[32];
-                        tc_ld32(t_lane + g * 32, r);
-                        tc_wait_ld();
-                        float v[32];
+                    float fr[2], ph[2];
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const int c = g * 32 + j4 * 4;
-                            const float4 fr = __ldg(reinterpret_cast<const float4*>(fl + c));
-                            const float4 ph = __ldg(reinterpret_cast<const float4*>(fl + FN_H + c));
-                            const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c));
-                            v[j4 * 4 + 0] = __sinf(fmaf(fr.x, __uint_as_float(r[j4 * 4 + 0]) + bs.x, ph.x));
-                            v[j4 * 4 + 1] = __sinf(fmaf(fr.y, __uint_as_float(r[j4 * 4 + 1]) + bs.y, ph.y));
-                            v[j4 * 4 + 2] = __sinf(fmaf(fr.z, __uint_as_float(r[j4 * 4 + 2]) + bs.z, ph.z));
-                            v[j4 * 4 + 3] = __sinf(fmaf(fr.w, __uint_as_float(r[j4 * 4 + 3]) + bs.w, ph.w));
-                        }
-                        if (sop.epi == EPI_FILM_SIGMA) {
+                    for (int h = 0; h < 2; ++h) {
+                        fr[h] = __ldg(film_l + h * 128 + fl);
+                        ph[h] = fmaf(fr[h], __ldg(bias + h * 128 + fl), __ldg(film_l + FN_H + h * 128 + fl));
+                    }
+                    mbar_wait(bar_acc, n_acc & 1);
+                    ++n_acc;
+                    tc_fence_after();
+                    tr.log('W', tl, s, 0);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) sigma = fmaf(v[j], __ldg(sigma_w + g * 32 + j), sigma);
-                        }
-                        if (sop.epi == EPI_FILM_RGB) {
+                    for (int h = 0; h < 2; ++h) {
+                        // element (point p, feature f = h*128 + fl) -> chunk f/64, k = f%64
+                        const uint32_t kk = (uint32_t)(fl & 63);
+                        unsigned char* chunk = smem + SMEM_A + (uint32_t)(h * 2 + (fl >> 6)) * A_CHUNK_BYTES + (kk & 7u) * 2u;
+                        const uint32_t kc = kk >> 3;
+                        const float f_h = fr[h], p_h = ph[h];
+                        uint32_t r[2][32];
+                        tc_ld32(t_lane + h * 128, r[0]);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {          // 4 groups of 32 points
+                            tc_wait_ld();
+                            if (g + 1 < 4) tc_ld32(t_lane + h * 128 + (g + 1) * 32, r[(g + 1) & 1]);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                rgb0 = fmaf(v[j], __ldg(rgb_w + g * 32 + j), rgb0);
-                                rgb1 = fmaf(v[j], __ldg(rgb_w + FN_H + g * 32 + j), rgb1);
-                                rgb2 = fmaf(v[j], __ldg(rgb_w + 2 * FN_H + g * 32 + j), rgb2);
-                            }
-                        } else {
-                            // 32 columns = half of k-chunk (g / 2): four 16-byte pieces, swizzled
-                            unsigned char* chunk = smem + SMEM_A + (uint32_t)(g >> 1) * A_CHUNK_BYTES + row_off;
-#pragma unroll
-                            for (int j8 = 0; j8 < 4; ++j8) {
-                                uint4 pk;
-                                pk.x = pack_half2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-                                pk.y = pack_half2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-                                pk.z = pack_half2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-                                pk.w = pack_half2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-                                const uint32_t piece = (uint32_t)((g & 1) * 4 + j8);
-                                *reinterpret_cast<uint4*>(chunk + ((piece ^ sw) << 4)) = pk;
+                                const uint32_t p = (uint32_t)(g * 32 + j);
+                                const float v = __sinf(fmaf(f_h, __uint_as_float(r[g & 1][j]), p_h));
+                                const uint32_t off = (p >> 3) * 1024u + (p & 7u) * 128u + (((kc ^ (p & 7u)) & 7u) << 4);
+                                *reinterpret_cast<__half*>(chunk + off) = __float2half_rn(v);
                             }
                         }
                     }
-                    if (sop.epi == EPI_FILM_SIGMA && valid) a.out[flat * C + (C - 1)] = sigma;
-                    if (sop.epi == EPI_FILM_RGB && valid) {
-                        a.out[flat * C + L.label_dim + 0] = __fdividef(1.f, 1.f + __expf(-rgb0));
-                        a.out[flat * C + L.label_dim + 1] = __fdividef(1.f, 1.f + __expf(-rgb1));
-                        a.out[flat * C + L.label_dim + 2] = __fdividef(1.f, 1.f + __expf(-rgb2));
+                } else {
+                    mbar_wait(bar_acc, n_acc & 1);
+                    ++n_acc;
+                    tc_fence_after();
+                    tr.log('W', tl, s, 0);
+                    if (sop.epi == EPI_HEAD_TRUNK) {
+                        // columns: labels 0..L-1 (scaled), sigma at column L
+                        if (L.label_dim > 0) {
+                            uint32_t r[32];
+                            tc_ld32(t_lane, r);
+                            tc_wait_ld();
+                            if (valid) {
+                                const float inv_scale = __ldg(label_w + FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL);
+#pragma unroll
+                                for (int o = 0; o < 32; ++o) {
+                                    if (o < L.label_dim)
+                                        a.out[flat * C + o] = fmaf(__uint_as_float(r[o]), inv_scale, __ldg(label_w + FENERF_MAX_LABEL * FN_H + o));
+                                    else if (o == L.label_dim)
+                                        a.out[flat * C + (C - 1)] = __uint_as_float(r[o]) + __ldg(sigma_w + FN_H);
+                                }
+                            }
+                        } else {
+                            uint32_t r[8];
+                            tc_ld8(t_lane, r);
+                            tc_wait_ld();
+                            if (valid) a.out[flat * C + (C - 1)] = __uint_as_float(r[0]) + __ldg(sigma_w + FN_H);
+                        }
+                    } else {
+                        uint32_t r[8];
+                        tc_ld8(t_lane, r);
+                        tc_wait_ld();
+                        if (valid) {
+#pragma unroll
+                            for (int o = 0; o < 3; ++o) {
+                                const float x = __uint_as_float(r[o]) + __ldg(rgb_w + 3 * FN_H + o);
+                                a.out[flat * C + L.label_dim + o] = __fdividef(1.f, 1.f + __expf(-x));
+                            }
+                        }
                     }
                 }
+                tr.log('D', tl, s, 0);
                 if (s + 1 < a.n_stages) {
                     // next stage may overwrite the accumulator and read what was just written
                     fence_async_smem();
@@ -382,18 +429,39 @@ struct Program {
     bool ok;
 };
 
-void push_image_loads(FastArgs& A, size_t img_off, int a_chunk0, int n_chunks, bool first_of_stage) {
-    // a [256][64] image per k-chunk, loaded as two 128-row halves
+void push_image_loads(FastArgs& A, size_t img_off, int n_chunks, bool first_of_stage) {
+    // a [256 features][64 k] image per k-chunk, streamed as two 128-feature halves (A operand);
+    // half h accumulates into TMEM columns [128 h, 128 h + 128) = the 128 points of the tile
     for (int kc = 0; kc < n_chunks; ++kc)
         for (int half = 0; half < 2; ++half) {
             LoadOp& op = A.loads[A.n_loads++];
             op.src = (uint32_t)(img_off + (size_t)kc * FN_IMG_BYTES + (size_t)half * STAGE_BYTES);
             op.bytes = STAGE_BYTES / 16;
-            op.a_chunk = (uint8_t)(a_chunk0 + kc);
-            op.k0 = 0; op.nk = 4; op.n8 = 128 / 8; op.d_col = (uint16_t)(half * 128);
+            op.a_chunk = (uint8_t)kc;
+            op.k0 = 0; op.nk = 4; op.n8 = TILE / 8; op.d_col = (uint16_t)(half * 128);
             op.first = (first_of_stage && kc == 0) ? 1 : 0;
-            op.last = 0;
+            op.last = 0; op.w_is_a = 1;
         }
+}
+
+void push_input_loads(FastArgs& A, size_t img_off, int k0, int nk, bool first) {
+    for (int half = 0; half < 2; ++half) {
+        LoadOp& op = A.loads[A.n_loads++];
+        op.src = (uint32_t)(img_off + (size_t)half * STAGE_BYTES);
+        op.bytes = STAGE_BYTES / 16; op.a_chunk = 4; op.k0 = (uint8_t)k0; op.nk = (uint8_t)nk; op.n8 = TILE / 8;
+        op.d_col = (uint16_t)(half * 128); op.first = first ? 1 : 0; op.last = 0; op.w_is_a = 1;
+    }
+}
+
+void push_head_loads(FastArgs& A, size_t img_off, int img_rows, int n) {
+    // head image [img_rows][64 k] per k-chunk is the B operand (N = n <= img_rows), the activation
+    // tile the A operand: D[point][head] in TMEM columns [0, n)
+    for (int kc = 0; kc < 4; ++kc) {
+        LoadOp& op = A.loads[A.n_loads++];
+        op.src = (uint32_t)(img_off + (size_t)kc * ((size_t)img_rows * FN_KCHUNK * 2));
+        op.bytes = (uint16_t)((n * FN_KCHUNK * 2) / 16); op.a_chunk = (uint8_t)kc; op.k0 = 0; op.nk = 4; op.n8 = (uint8_t)(n / 8);
+        op.d_col = 0; op.first = kc == 0; op.last = 0; op.w_is_a = 0;
+    }
 }
 
 bool build_program(const FnLayout& L, FastArgs& A) {
@@ -406,47 +474,38 @@ bool build_program(const FnLayout& L, FastArgs& A) {
     // first layer: only K-step 0 of the input chunk (position hi/lo slots)
     {
         int l0 = A.n_loads;
-        for (int half = 0; half < 2; ++half) {
-            LoadOp& op = A.loads[A.n_loads++];
-            op.src = (uint32_t)(L.first_img + (size_t)half * STAGE_BYTES);
-            op.bytes = STAGE_BYTES / 16; op.a_chunk = 4; op.k0 = 0; op.nk = 1; op.n8 = 16; op.d_col = (uint16_t)(half * 128);
-            op.first = 1; op.last = 0;
-        }
+        push_input_loads(A, L.first_img, 0, 1, true);
         end_stage(EPI_FILM, 0, l0);
     }
     for (int l = 0; l < L.n_hidden; ++l) {
-        if (l == L.trunk_hidden && L.label_dim > 0) {
+        if (l == L.trunk_hidden) {
+            // heads on the trunk output: labels (if any) + sigma
             int l0 = A.n_loads;
-            for (int kc = 0; kc < 4; ++kc) {
-                LoadOp& op = A.loads[A.n_loads++];
-                op.src = (uint32_t)(L.label_img + (size_t)kc * (32 * FN_KCHUNK * 2));
-                op.bytes = (32 * FN_KCHUNK * 2) / 16; op.a_chunk = (uint8_t)kc; op.k0 = 0; op.nk = 4; op.n8 = 32 / 8; op.d_col = 0;
-                op.first = kc == 0; op.last = 0;
-            }
-            end_stage(EPI_LABEL, 0, l0);
+            push_head_loads(A, L.head_img, 32, L.label_dim > 0 ? 32 : 8);
+            end_stage(EPI_HEAD_TRUNK, 0, l0);
         }
         int l0 = A.n_loads;
-        push_image_loads(A, L.hid_img[l], 0, 4, true);
-        if (l == L.trunk_hidden) {
-            // extra inputs of the first colour layer: K-steps 1.. of the input chunk (dir, then grid features)
-            const int nk = L.grid_channels > 0 ? 3 : 1;
-            for (int half = 0; half < 2; ++half) {
-                LoadOp& op = A.loads[A.n_loads++];
-                op.src = (uint32_t)(L.color0_ximg + (size_t)half * STAGE_BYTES);
-                op.bytes = STAGE_BYTES / 16; op.a_chunk = 4; op.k0 = 1; op.nk = (uint8_t)nk; op.n8 = 16; op.d_col = (uint16_t)(half * 128);
-                op.first = 0; op.last = 0;
-            }
-        }
-        uint8_t epi = EPI_FILM;
-        if (l == L.trunk_hidden - 1) epi = EPI_FILM_SIGMA;
-        if (l == L.n_hidden - 1) epi = EPI_FILM_RGB;
-        end_stage(epi, (uint8_t)(l + 1), l0);
-        if (A.n_loads > MAX_LOADS - 12 || A.n_stages > MAX_STAGES - 2) return false;
+        push_image_loads(A, L.hid_img[l], 4, true);
+        if (l == L.trunk_hidden)   // first colour layer: view direction (+ grid features) from the input chunk
+            push_input_loads(A, L.color0_ximg, 1, L.grid_channels > 0 ? 3 : 1, false);
+        end_stage(EPI_FILM, (uint8_t)(l + 1), l0);
+        if (A.n_loads > MAX_LOADS - 16 || A.n_stages > MAX_STAGES - 3) return false;
+    }
+    {
+        int l0 = A.n_loads;
+        push_head_loads(A, L.rgb_img, 8, 8);
+        end_stage(EPI_HEAD_RGB, 0, l0);
     }
     return true;
 }
 
 }  // namespace
+
+namespace {
+long long* g_trace = nullptr;
+}  // namespace
+
+void set_fast_trace(long long* buf) { g_trace = buf; }
 
 int siren_points_fast(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
@@ -454,13 +513,14 @@ int siren_points_fast(const FnLayout& L, const unsigned char* packed, const floa
     static_assert(sizeof(FastArgs) <= 4000, "kernel parameter block too large");
     static_assert(SMEM_TOTAL <= 115712, "two CTAs per SM must fit");
     FN_REQUIRE(L.trunk_hidden >= 1 && L.n_hidden - L.trunk_hidden >= 1, "field needs >= 2 trunk and >= 1 colour layers");
-    FN_REQUIRE(L.trunk_hidden - 1 != L.n_hidden - 1, "internal: sigma and rgb epilogues coincide");
+    FN_REQUIRE(L.label_dim < 32, "the tcgen05 path packs labels and sigma into one 32-row head (label_dim <= 31)");
     FastArgs a;
     memset(&a, 0, sizeof(a));
     FN_REQUIRE(build_program(L, a), "field too deep for the stage program");
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out;
     a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
     a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs;
+    a.trace = g_trace;
     if (a.n_tiles <= 0) return 0;
     FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);
     FN_CUDA_OK(cudaFuncSetAttribute(siren_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
