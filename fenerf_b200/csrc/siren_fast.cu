@@ -1,15 +1,26 @@
 // Point network, FAST mode: the FiLM-SIREN stack on the 5th-generation tensor cores.
 //
 // Replaces <SIREN>.forward_with_frequencies_phase_shifts (siren/siren.py:164-178, 1509-1530).
-// One persistent CTA (two per SM) walks 128-point tiles; per tile every FiLM layer is
+// One persistent CTA per SM walks PAIRS of 128-point tiles; per tile every FiLM layer is
 //     tcgen05.mma (fp16 operands, fp32 accumulator in TMEM)  ->  epilogue warps:
 //     tcgen05.ld, sin(freq * (acc + b) + phase), fp16, written back as the next layer's operand
 // so activations never leave the SM.  Weights are pre-swizzled UMMA images in HBM/L2 (pack.cu) and
 // stream through a shared-memory ring with 1-D bulk copies (cp.async.bulk, the TMA engine).
 //
-//   warp 0       weight producer     cp.async.bulk global -> ring stage, arms full[stage]
-//   warp 1       MMA issuer          one elected lane issues tcgen05.mma / tcgen05.commit; owns TMEM
-//   warps 2..5   epilogue            128 threads
+//   warps 0..3   weight producers    warp w owns ring slot w: cp.async.bulk global -> slot, arms full[w]
+//   warp 4       MMA issuer          one elected lane issues tcgen05.mma / tcgen05.commit; owns TMEM
+//   warps 5..8   epilogue of tile X  128 threads
+//   warps 9..12  epilogue of tile Y  128 threads
+// (One thread can start only one bulk copy per ~680 cycles whatever its size -- 24 B/clk for 16 KB
+// copies -- while four issuing warps reach ~90 B/clk/SM: tools/bulk_bench.cu, profiles/r01_bulk_bench.txt.
+// Hence one producer warp per ring slot.)
+//
+// Two tiles, one ring.  A bulk copy from L2 has a ~1600-cycle turnaround per ring slot regardless of
+// its size (profiles/r01_trace_v2*.txt), so the weight stream is latency bound and what counts is
+// bytes in flight.  The two tiles of a CTA run the same layer program half a layer apart: while X's
+// epilogue warps turn its accumulator into the next activations, the MMA issuer streams Y's layer
+// through the WHOLE 4-slot ring, and vice versa -- each tile sees a 64 KB ring during its MMA phase
+// and the tensor pipe, the MUFU pipe and the copy engine overlap inside one CTA.
 //
 // Orientation.  The FiLM layers run TRANSPOSED: D^T[feature][point] = W[feature][k] . X[point][k],
 // i.e. the weight image is the MMA's A operand (M = 128 features per half) and the activation tile
@@ -28,10 +39,10 @@
 // Tensor-pipe bound by design (2*256*256 FLOP per point per layer); co-limited by MUFU (one sin per
 // output element, 16/clk/SM) and by the L2->SM weight stream (128 KB per layer per 128-point tile).
 //
-// Shared memory (<= 113 KB so two CTAs share an SM; TMEM 256 columns each):
-//   A     4 x 16 KB   activations [128 points][64 k] f16 x 4 k-chunks, 128B swizzle, K-major
-//   X     16 KB       input chunk [128 points][64 slots]   (layout.h: slot order)
-//   ring  2 x 16 KB   weight stages [128 feature rows][64 k] (half of one k-chunk image)
+// Shared memory (224 KB, one CTA per SM; TMEM 2 x 256 columns):
+//   A     2 x 4 x 16 KB  activations [128 points][64 k] f16 x 4 k-chunks per tile, 128B swizzle, K-major
+//   X     2 x 16 KB      input chunk [128 points][64 slots] per tile   (layout.h: slot order)
+//   ring  4 x 16 KB      weight stages [128 feature rows][64 k] (half of one k-chunk image)
 #include "common.cuh"
 #include "siren_common.cuh"
 
@@ -40,16 +51,18 @@ namespace fn {
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NTHREADS = 192;
-constexpr int RING = 2;
+constexpr int NTHREADS = 416;
+constexpr int MMA_WARP = 4, EPI_WARP0 = 5;
+constexpr int RING = 4;
 constexpr uint32_t STAGE_BYTES = 16384;
 constexpr uint32_t A_CHUNK_BYTES = 16384;
-constexpr uint32_t SMEM_A = 0;
-constexpr uint32_t SMEM_X = 4 * A_CHUNK_BYTES;
-constexpr uint32_t SMEM_RING = SMEM_X + A_CHUNK_BYTES;
-constexpr uint32_t SMEM_BAR = SMEM_RING + RING * STAGE_BYTES;   // 114688
+constexpr uint32_t TILE_SMEM = 5 * A_CHUNK_BYTES;               // 4 activation chunks + the input chunk
+constexpr uint32_t SMEM_A = 0;                                  // + t * TILE_SMEM
+constexpr uint32_t SMEM_X = 4 * A_CHUNK_BYTES;                  // + t * TILE_SMEM
+constexpr uint32_t SMEM_RING = 2 * TILE_SMEM;
+constexpr uint32_t SMEM_BAR = SMEM_RING + RING * STAGE_BYTES;   // 229376
 constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 128;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;                                  // 256 accumulator columns per tile
 constexpr int MAX_LOADS = 128;
 constexpr int MAX_STAGES = 16;
 
@@ -65,14 +78,14 @@ struct LoadOp {            // one ring stage: a bulk copy and the MMAs that cons
     uint8_t first;         // 1: first MMA of this accumulator range (overwrite instead of accumulate)
     uint8_t last;          // 1: last load of its stage -> commit the accumulator
     uint8_t w_is_a;        // 1: ring stage is the A operand (transposed FiLM layer); 0: it is B (head)
-    uint8_t pad;
+    uint8_t n_chunks;      // k-chunks packed in this one load (heads: 4, each `bytes / 4` apart), else 1
 };
 
 struct StageOp {
     uint8_t epi;           // EPI_*
     uint8_t film;          // FiLM layer index
     uint8_t n_loads;
-    uint8_t pad;
+    uint8_t uniform;       // 1: the first 8 loads are the canonical 4 k-chunks x 2 halves of a 256x256 image
 };
 
 struct FastArgs {
@@ -131,6 +144,18 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Warp-converged variants: every lane executes the call with identical (warp-uniform) operands and
+// one elected lane issues.  Keeps the issuer loop out of divergent code, so operands stay in uniform
+// registers instead of being re-broadcast (R2UR + ELECT loop) around every instruction.
+__device__ __forceinline__ void tc_mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -159,8 +184,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= 2ull << 61;
     return d;
 }
+// the constant upper word of umma_desc_sw128: SBO 1024 B, version 1, SWIZZLE_128B
+constexpr uint64_t kDescHi = ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 // instruction descriptor, kind::f16: D f32, A/B f16, both K-major, M = 128
-__device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t n) {
     return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
@@ -174,32 +201,36 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 }
 
 // Diagnostics: CTA 0 logs (tag, clock64) pairs for its first tiles; one 4096-entry lane per role.
+template <bool kOn>
 struct Tracer {
     long long* p; int n;
-    __device__ Tracer(long long* base, int role) : p(base && blockIdx.x == 0 ? base + role * 4096 : nullptr), n(0) {}
+    __device__ Tracer(long long* base, int role) : p(kOn && base && blockIdx.x == 0 ? base + role * 4096 : nullptr), n(0) {}
     __device__ __forceinline__ void log(int kind, int tile, int stage, int item) {
-        if (p && tile < 2 && n < 2040) { p[2 + 2 * n] = ((long long)kind << 48) | ((long long)tile << 32) | (stage << 16) | item; p[3 + 2 * n] = clock64(); ++n; p[0] = n; }
+        if (kOn && p && tile < 2 && n < 2040) { p[2 + 2 * n] = ((long long)kind << 48) | ((long long)tile << 32) | (stage << 16) | item; p[3 + 2 * n] = clock64(); ++n; p[0] = n; }
     }
 };
 
 // ---- the kernel -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_constant__ FastArgs a) {
+template <bool kTrace>
+__global__ void __launch_bounds__(NTHREADS, 1) siren_fast_kernel(const __grid_constant__ FastArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = sbase + SMEM_BAR;            // RING x 8 B
     const uint32_t bar_empty = bar_full + 8 * RING;        // RING x 8 B
-    const uint32_t bar_acc = bar_empty + 8 * RING;         // accumulator ready (MMA -> epilogue)
-    const uint32_t bar_aready = bar_acc + 8;               // A operand ready + TMEM drained (epilogue -> MMA)
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * RING + 2));
+    const uint32_t bar_acc = bar_empty + 8 * RING;         // [2] accumulator ready (MMA -> epilogue of tile t)
+    const uint32_t bar_aready = bar_acc + 16;              // [2] operand ready + TMEM drained (epilogue t -> MMA)
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * RING + 4));
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_aready, 4);      // one arrival per epilogue warp
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar_acc + 8 * t, 1);
+            mbar_init(bar_aready + 8 * t, 4);      // one arrival per epilogue warp of the tile
+        }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32((const void*)tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -210,63 +241,114 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
     const FnLayout& L = a.L;
 
-    if (warp == 0) {
-        // ================= weight producer =================
+    if (warp < RING) {
+        // ================= weight producers =================
+        // job order (shared with the MMA issuer): for each pair, for each stage, tile X then tile Y;
+        // load number `it` lives in ring slot it % RING and is issued by producer warp it % RING
         if (lane == 0) {
             uint32_t it = 0;
-            Tracer tr(a.trace, 0);
+            Tracer<kTrace> tr(warp == 0 ? a.trace : nullptr, 0);
             int tl = 0;
-            for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
-                for (int i = 0; i < a.n_loads; ++i, ++it) {
-                    const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                    mbar_wait(bar_empty + 8 * slot, ph ^ 1);
-                    tr.log('E', tl, 0, i);
-                    const uint32_t bytes = (uint32_t)a.loads[i].bytes * 16u;
-                    mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-                    bulk_g2s(sbase + SMEM_RING + slot * STAGE_BYTES, a.packed + a.loads[i].src, bytes, bar_full + 8 * slot);
+            for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x, ++tl) {
+                const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
+                int li = 0;
+                for (int s = 0; s < a.n_stages; ++s) {
+                    for (int t = 0; t < nt; ++t)
+                        for (int j = 0; j < a.stages[s].n_loads; ++j, ++it) {
+                            const int i = li + j;
+                            const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                            if (slot != (uint32_t)warp) continue;
+                            mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+                            tr.log('E', tl, s, t * 64 + j);
+                            const uint32_t bytes = (uint32_t)a.loads[i].bytes * 16u;
+                            mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+                            bulk_g2s(sbase + SMEM_RING + slot * STAGE_BYTES, a.packed + a.loads[i].src, bytes, bar_full + 8 * slot);
+                            tr.log('B', tl, s, t * 64 + j);
+                        }
+                    li += a.stages[s].n_loads;
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t it = 0, n_ready = 0;
-            Tracer tr(a.trace, 1);
+        // the whole warp runs this loop converged; an elected lane issues (tc_*_elect)
+        {
+            uint32_t it = 0, n_ready[2] = {0, 0};
+            Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, 1);
             int tl = 0;
-            for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
-                int li = 0;
+            for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x, ++tl) {
+                const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
+                int li0 = 0;
                 for (int s = 0; s < a.n_stages; ++s) {
-                    mbar_wait(bar_aready, n_ready & 1);     // inputs written, accumulator drained
-                    ++n_ready;
-                    tc_fence_after();
-                    tr.log('A', tl, s, 0);
-                    for (int j = 0; j < a.stages[s].n_loads; ++j, ++li, ++it) {
-                        const LoadOp op = a.loads[li];
-                        const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                        mbar_wait(bar_full + 8 * slot, ph);
+                    for (int t = 0; t < nt; ++t) {
+                        mbar_wait(bar_aready + 8 * t, n_ready[t] & 1);     // inputs written, accumulator drained
+                        ++n_ready[t];
                         tc_fence_after();
-                        tr.log('F', tl, s, li);
-                        const uint32_t x_addr = sbase + (op.a_chunk < 4 ? SMEM_A + op.a_chunk * A_CHUNK_BYTES : SMEM_X);
-                        const uint32_t w_addr = sbase + SMEM_RING + slot * STAGE_BYTES;
-                        const uint32_t a_addr = op.w_is_a ? w_addr : x_addr;
-                        const uint32_t b_addr = op.w_is_a ? x_addr : w_addr;
-                        const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u);
-                        for (int k = 0; k < op.nk; ++k) {
-                            const uint32_t koff = (uint32_t)(op.k0 + k) * 32u;      // 16 f16 = 32 B inside the swizzle row
-                            tc_mma_f16(tmem_base + op.d_col, umma_desc_sw128(a_addr + koff), umma_desc_sw128(b_addr + koff),
-                                       idesc, (op.first && k == 0) ? 0u : 1u);
+                        tr.log('A', tl, s, t);
+                        const StageOp sop = a.stages[s];
+                        int j0 = 0;
+                        if (sop.uniform) {
+                            // straight-line issue for a 256x256 FiLM layer: 4 k-chunks x 2 feature halves,
+                            // every descriptor word is a base plus a compile-time constant
+                            const uint32_t x_lo = (sbase + t * TILE_SMEM + SMEM_A) >> 4;       // activation chunk 0, K-step 0
+                            const uint32_t d0 = tmem_base + t * 256;
+                            const uint32_t idesc = umma_idesc_f16(TILE);
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj, ++it) {
+                                const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                                mbar_wait(bar_full + 8 * slot, ph);
+                                tc_fence_after();
+                                tr.log('F', tl, s, t * 64 + jj);
+                                const uint32_t w_lo = (sbase + SMEM_RING + slot * STAGE_BYTES) >> 4;
+                                const uint32_t xk_lo = x_lo + (uint32_t)(jj >> 1) * (A_CHUNK_BYTES >> 4);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma_f16_elect(d0 + (jj & 1) * 128, kDescHi | (uint64_t)(w_lo + 2 * k), kDescHi | (uint64_t)(xk_lo + 2 * k),
+                                               idesc, (jj < 2 && k == 0) ? 0u : 1u);
+                                tr.log('M', tl, s, t * 64 + jj);
+                                tc_commit_elect(bar_empty + 8 * slot);
+                                if (jj == 7 && sop.n_loads == 8) { tc_commit_elect(bar_acc + 8 * t); tr.log('C', tl, s, t); }
+                            }
+                            j0 = 8;
                         }
-                        tc_commit(bar_empty + 8 * slot);      // ring stage reusable once these MMAs retire
-                        if (op.last) { tc_commit(bar_acc); tr.log('C', tl, s, li); }   // accumulator complete for this stage
+                        for (int j = j0; j < sop.n_loads; ++j, ++it) {
+                            const LoadOp op = a.loads[li0 + j];
+                            const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                            mbar_wait(bar_full + 8 * slot, ph);
+                            tc_fence_after();
+                            tr.log('F', tl, s, t * 64 + j);
+                            const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u);
+                            const uint32_t w_stride = ((uint32_t)op.bytes * 16u) / op.n_chunks;
+                            for (int c = 0; c < op.n_chunks; ++c) {
+                                const int xc = op.a_chunk + c;
+                                const uint32_t x_addr = sbase + t * TILE_SMEM + (xc < 4 ? SMEM_A + xc * A_CHUNK_BYTES : SMEM_X);
+                                const uint32_t w_addr = sbase + SMEM_RING + slot * STAGE_BYTES + c * w_stride;
+                                const uint32_t a_addr = op.w_is_a ? w_addr : x_addr;
+                                const uint32_t b_addr = op.w_is_a ? x_addr : w_addr;
+                                for (int k = 0; k < op.nk; ++k) {
+                                    const uint32_t koff = (uint32_t)(op.k0 + k) * 32u;   // 16 f16 = 32 B inside the swizzle row
+                                    tc_mma_f16_elect(tmem_base + t * 256 + op.d_col, umma_desc_sw128(a_addr + koff),
+                                               umma_desc_sw128(b_addr + koff), idesc, (op.first && c == 0 && k == 0) ? 0u : 1u);
+                                }
+                            }
+                            tr.log('M', tl, s, t * 64 + j);
+                            tc_commit_elect(bar_empty + 8 * slot);      // ring stage reusable once these MMAs retire
+                            tr.log('K', tl, s, t * 64 + j);
+                            if (op.last) { tc_commit_elect(bar_acc + 8 * t); tr.log('C', tl, s, t); }
+                        }
                     }
+                    li0 += a.stages[s].n_loads;
                 }
             }
         }
     } else {
         // ================= epilogue warps =================
+        const int t = (warp - EPI_WARP0) >> 2;        // which tile of the pair this warp serves
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-        const int row = q * 32 + lane;                // point slot in the tile
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int row = q * 32 + lane;                // point slot in the tile / feature within a half
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+        unsigned char* tsm = smem + t * TILE_SMEM;    // this tile's activation + input chunks
+        const uint32_t my_acc = bar_acc + 8 * t, my_aready = bar_aready + 8 * t;
         const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
         const uint32_t sw = (uint32_t)(row & 7);
         const int C = L.out_dim;
@@ -274,9 +356,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
         const float* rgb_w = reinterpret_cast<const float*>(a.packed + L.rgb_w);
         const float* label_w = reinterpret_cast<const float*>(a.packed + L.label_w);
         uint32_t n_acc = 0;
-        Tracer tr(warp == 2 && lane == 0 ? a.trace : nullptr, 2);
+        Tracer<kTrace> tr((warp == EPI_WARP0 || warp == EPI_WARP0 + 4) && lane == 0 ? a.trace : nullptr, 2 + t);
         int tl = 0;
-        for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
+        for (long long pair = blockIdx.x; pair * 2 + t < a.n_tiles; pair += gridDim.x, ++tl) {
+            const long long tile = pair * 2 + t;
             tr.log('T', tl, 0, 0);
             // ---- build the input chunk for this tile ----
             const long long b = tile / a.tiles_per_batch;
@@ -315,12 +398,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
                 const uint4* src = reinterpret_cast<const uint4*>(slots);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(smem + SMEM_X + row_off + (((uint32_t)j ^ sw) << 4)) = src[j];
+                    *reinterpret_cast<uint4*>(tsm + SMEM_X + row_off + (((uint32_t)j ^ sw) << 4)) = src[j];
             }
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_aready);
+            if (lane == 0) mbar_arrive(my_aready);
 
             for (int s = 0; s < a.n_stages; ++s) {
                 const StageOp sop = a.stages[s];
@@ -337,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
                         fr[h] = __ldg(film_l + h * 128 + fl);
                         ph[h] = fmaf(fr[h], __ldg(bias + h * 128 + fl), __ldg(film_l + FN_H + h * 128 + fl));
                     }
-                    mbar_wait(bar_acc, n_acc & 1);
+                    mbar_wait(my_acc, n_acc & 1);
                     ++n_acc;
                     tc_fence_after();
                     tr.log('W', tl, s, 0);
@@ -345,7 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
                     for (int h = 0; h < 2; ++h) {
                         // element (point p, feature f = h*128 + fl) -> chunk f/64, k = f%64
                         const uint32_t kk = (uint32_t)(fl & 63);
-                        unsigned char* chunk = smem + SMEM_A + (uint32_t)(h * 2 + (fl >> 6)) * A_CHUNK_BYTES + (kk & 7u) * 2u;
+                        unsigned char* chunk = tsm + SMEM_A + (uint32_t)(h * 2 + (fl >> 6)) * A_CHUNK_BYTES + (kk & 7u) * 2u;
                         const uint32_t kc = kk >> 3;
                         const float f_h = fr[h], p_h = ph[h];
                         uint32_t r[2][32];
@@ -364,7 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
                         }
                     }
                 } else {
-                    mbar_wait(bar_acc, n_acc & 1);
+                    mbar_wait(my_acc, n_acc & 1);
                     ++n_acc;
                     tc_fence_after();
                     tr.log('W', tl, s, 0);
@@ -409,7 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_aready);
+                    if (lane == 0) mbar_arrive(my_aready);
                 }
             }
         }
@@ -417,7 +500,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_fast_kernel(const __grid_co
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
@@ -440,7 +523,7 @@ void push_image_loads(FastArgs& A, size_t img_off, int n_chunks, bool first_of_s
             op.a_chunk = (uint8_t)kc;
             op.k0 = 0; op.nk = 4; op.n8 = TILE / 8; op.d_col = (uint16_t)(half * 128);
             op.first = (first_of_stage && kc == 0) ? 1 : 0;
-            op.last = 0; op.w_is_a = 1;
+            op.last = 0; op.w_is_a = 1; op.n_chunks = 1;
         }
 }
 
@@ -449,26 +532,25 @@ void push_input_loads(FastArgs& A, size_t img_off, int k0, int nk, bool first) {
         LoadOp& op = A.loads[A.n_loads++];
         op.src = (uint32_t)(img_off + (size_t)half * STAGE_BYTES);
         op.bytes = STAGE_BYTES / 16; op.a_chunk = 4; op.k0 = (uint8_t)k0; op.nk = (uint8_t)nk; op.n8 = TILE / 8;
-        op.d_col = (uint16_t)(half * 128); op.first = first ? 1 : 0; op.last = 0; op.w_is_a = 1;
+        op.d_col = (uint16_t)(half * 128); op.first = first ? 1 : 0; op.last = 0; op.w_is_a = 1; op.n_chunks = 1;
     }
 }
 
 void push_head_loads(FastArgs& A, size_t img_off, int img_rows, int n) {
-    // head image [img_rows][64 k] per k-chunk is the B operand (N = n <= img_rows), the activation
-    // tile the A operand: D[point][head] in TMEM columns [0, n)
-    for (int kc = 0; kc < 4; ++kc) {
-        LoadOp& op = A.loads[A.n_loads++];
-        op.src = (uint32_t)(img_off + (size_t)kc * ((size_t)img_rows * FN_KCHUNK * 2));
-        op.bytes = (uint16_t)((n * FN_KCHUNK * 2) / 16); op.a_chunk = (uint8_t)kc; op.k0 = 0; op.nk = 4; op.n8 = (uint8_t)(n / 8);
-        op.d_col = 0; op.first = kc == 0; op.last = 0; op.w_is_a = 0;
-    }
+    // the head image [4 k-chunks][img_rows][64 k] is the B operand (N = n <= img_rows), the activation
+    // tile the A operand: D[point][head] in TMEM columns [0, n).  All four k-chunks travel in ONE
+    // bulk copy: a slot's turnaround does not depend on its size.
+    LoadOp& op = A.loads[A.n_loads++];
+    op.src = (uint32_t)img_off;
+    op.bytes = (uint16_t)((4 * img_rows * FN_KCHUNK * 2) / 16); op.a_chunk = 0; op.k0 = 0; op.nk = 4; op.n8 = (uint8_t)(n / 8);
+    op.d_col = 0; op.first = 1; op.last = 0; op.w_is_a = 0; op.n_chunks = 4;
 }
 
 bool build_program(const FnLayout& L, FastArgs& A) {
     A.n_loads = 0; A.n_stages = 0;
     auto end_stage = [&](uint8_t epi, uint8_t film, int first_load) {
         StageOp& st = A.stages[A.n_stages++];
-        st.epi = epi; st.film = film; st.n_loads = (uint8_t)(A.n_loads - first_load); st.pad = 0;
+        st.epi = epi; st.film = film; st.n_loads = (uint8_t)(A.n_loads - first_load); st.uniform = 0;
         A.loads[A.n_loads - 1].last = 1;
     };
     // first layer: only K-step 0 of the input chunk (position hi/lo slots)
@@ -489,6 +571,7 @@ bool build_program(const FnLayout& L, FastArgs& A) {
         if (l == L.trunk_hidden)   // first colour layer: view direction (+ grid features) from the input chunk
             push_input_loads(A, L.color0_ximg, 1, L.grid_channels > 0 ? 3 : 1, false);
         end_stage(EPI_FILM, (uint8_t)(l + 1), l0);
+        A.stages[A.n_stages - 1].uniform = 1;
         if (A.n_loads > MAX_LOADS - 16 || A.n_stages > MAX_STAGES - 3) return false;
     }
     {
@@ -511,7 +594,7 @@ int siren_points_fast(const FnLayout& L, const unsigned char* packed, const floa
                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
                       cudaStream_t st) {
     static_assert(sizeof(FastArgs) <= 4000, "kernel parameter block too large");
-    static_assert(SMEM_TOTAL <= 115712, "two CTAs per SM must fit");
+    static_assert(SMEM_TOTAL <= 232448, "one CTA per SM: 227 KB of shared memory");
     FN_REQUIRE(L.trunk_hidden >= 1 && L.n_hidden - L.trunk_hidden >= 1, "field needs >= 2 trunk and >= 1 colour layers");
     FN_REQUIRE(L.label_dim < 32, "the tcgen05 path packs labels and sigma into one 32-row head (label_dim <= 31)");
     FastArgs a;
@@ -519,13 +602,15 @@ int siren_points_fast(const FnLayout& L, const unsigned char* packed, const floa
     FN_REQUIRE(build_program(L, a), "field too deep for the stage program");
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out;
     a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
+    const long long n_pairs = (a.n_tiles + 1) / 2;
     a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs;
     a.trace = g_trace;
     if (a.n_tiles <= 0) return 0;
     FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);
-    FN_CUDA_OK(cudaFuncSetAttribute(siren_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-    int blocks = (int)(a.n_tiles < (long long)num_sms() * 2 ? a.n_tiles : (long long)num_sms() * 2);
-    siren_fast_kernel<<<blocks, NTHREADS, SMEM_TOTAL, st>>>(a);
+    auto kernel = a.trace ? siren_fast_kernel<true> : siren_fast_kernel<false>;
+    FN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    int blocks = (int)(n_pairs < (long long)num_sms() ? n_pairs : (long long)num_sms());
+    kernel<<<blocks, NTHREADS, SMEM_TOTAL, st>>>(a);
     FN_LAUNCH_OK("siren_fast_kernel");
     return 0;
 }

@@ -212,9 +212,10 @@ const char* fenerf_last_error(void);
 int32_t fenerf_abi_version(void);
 int64_t fenerf_launch_count(void);
 
-/* Diagnostics: install a device buffer of 3 * 4096 int64 that CTA 0 of the tcgen05 point-network
- * kernel fills with (tag, clock64) pairs for its first two tiles, one 4096-entry lane per warp role
- * (producer, MMA issuer, epilogue); NULL (the default) disables.  Process-wide, not thread-safe. */
+/* Diagnostics: install a device buffer of 4 * 4096 int64 that CTA 0 of the tcgen05 point-network
+ * kernel fills with (tag, clock64) pairs for its first two tile pairs, one 4096-entry lane per warp
+ * role (producer, MMA issuer, epilogue X, epilogue Y); NULL (the default) disables.  Process-wide,
+ * not thread-safe. */
 void fenerf_debug_trace(void* device_buffer);
 
 #ifdef __cplusplus
