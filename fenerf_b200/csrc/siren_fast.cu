@@ -246,26 +246,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast_kernel(const __grid_co
         // job order (shared with the MMA issuer): for each pair, for each stage, tile X then tile Y;
         // load number `it` lives in ring slot it % RING and is issued by producer warp it % RING
         if (lane == 0) {
-            uint32_t it = 0;
+            // Ring slots are assigned per stage: load j of a (stage, tile) job lives in slot j % RING, so
+            // the MMA issuer's unrolled code addresses the ring with immediates.  Each slot keeps its own
+            // use count (phase parity), identical here and in the issuer.
+            uint32_t uses = 0;                       // completed uses of MY slot
             Tracer<kTrace> tr(warp == 0 ? a.trace : nullptr, 0);
             int tl = 0;
             for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x, ++tl) {
                 const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
                 int li = 0;
                 for (int s = 0; s < a.n_stages; ++s) {
+                    const int n = a.stages[s].n_loads;
                     for (int t = 0; t < nt; ++t)
-                        for (int j = 0; j < a.stages[s].n_loads; ++j, ++it) {
+                        for (int j = warp; j < n; j += RING, ++uses) {
                             const int i = li + j;
-                            const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                            if (slot != (uint32_t)warp) continue;
-                            mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+                            mbar_wait(bar_empty + 8 * warp, (uses & 1) ^ 1);
                             tr.log('E', tl, s, t * 64 + j);
                             const uint32_t bytes = (uint32_t)a.loads[i].bytes * 16u;
-                            mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-                            bulk_g2s(sbase + SMEM_RING + slot * STAGE_BYTES, a.packed + a.loads[i].src, bytes, bar_full + 8 * slot);
+                            mbar_arrive_expect_tx(bar_full + 8 * warp, bytes);
+                            bulk_g2s(sbase + SMEM_RING + warp * STAGE_BYTES, a.packed + a.loads[i].src, bytes, bar_full + 8 * warp);
                             tr.log('B', tl, s, t * 64 + j);
                         }
-                    li += a.stages[s].n_loads;
+                    li += n;
                 }
             }
         }
@@ -273,52 +275,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast_kernel(const __grid_co
         // ================= MMA issuer =================
         // the whole warp runs this loop converged; an elected lane issues (tc_*_elect)
         {
-            uint32_t it = 0, n_ready[2] = {0, 0};
+            uint32_t used[RING] = {0, 0, 0, 0};      // per-slot use counts (phase parity), see the producers
+            uint32_t n_ready[2] = {0, 0};
             Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, 1);
+            const uint32_t ring_lo = (sbase + SMEM_RING) >> 4;
             int tl = 0;
             for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x, ++tl) {
                 const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
                 int li0 = 0;
                 for (int s = 0; s < a.n_stages; ++s) {
+                    const StageOp sop = a.stages[s];
                     for (int t = 0; t < nt; ++t) {
                         mbar_wait(bar_aready + 8 * t, n_ready[t] & 1);     // inputs written, accumulator drained
                         ++n_ready[t];
                         tc_fence_after();
                         tr.log('A', tl, s, t);
-                        const StageOp sop = a.stages[s];
                         int j0 = 0;
                         if (sop.uniform) {
-                            // straight-line issue for a 256x256 FiLM layer: 4 k-chunks x 2 feature halves,
-                            // every descriptor word is a base plus a compile-time constant
-                            const uint32_t x_lo = (sbase + t * TILE_SMEM + SMEM_A) >> 4;       // activation chunk 0, K-step 0
+                            // straight-line issue for a 256x256 FiLM layer: 4 k-chunks x 2 feature halves in
+                            // ring slots 0,1,2,3,0,1,2,3; every descriptor word is a base plus an immediate.
+                            // The wait for load jj+1 sits between the MMAs of load jj.
+                            const uint32_t x_lo = (sbase + t * TILE_SMEM + SMEM_A) >> 4;
                             const uint32_t d0 = tmem_base + t * 256;
-                            const uint32_t idesc = umma_idesc_f16(TILE);
+                            constexpr uint32_t idesc = umma_idesc_f16(TILE);
+                            mbar_wait(bar_full, used[0] & 1);
+                            tc_fence_after();
 #pragma unroll
-                            for (int jj = 0; jj < 8; ++jj, ++it) {
-                                const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                                mbar_wait(bar_full + 8 * slot, ph);
-                                tc_fence_after();
+                            for (int jj = 0; jj < 8; ++jj) {
+                                constexpr uint32_t kStage16 = STAGE_BYTES >> 4, kChunk16 = A_CHUNK_BYTES >> 4;
+                                const int slot = jj & 3;
                                 tr.log('F', tl, s, t * 64 + jj);
-                                const uint32_t w_lo = (sbase + SMEM_RING + slot * STAGE_BYTES) >> 4;
-                                const uint32_t xk_lo = x_lo + (uint32_t)(jj >> 1) * (A_CHUNK_BYTES >> 4);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    tc_mma_f16_elect(d0 + (jj & 1) * 128, kDescHi | (uint64_t)(w_lo + 2 * k), kDescHi | (uint64_t)(xk_lo + 2 * k),
-                                               idesc, (jj < 2 && k == 0) ? 0u : 1u);
+                                for (int k = 0; k < 4; ++k) {
+                                    if (k == 2 && jj < 7) {
+                                        const int nslot = (jj + 1) & 3;
+                                        mbar_wait(bar_full + 8 * nslot, (used[nslot] + (jj + 1 >= 4 ? 1 : 0)) & 1);
+                                        tc_fence_after();
+                                    }
+                                    tc_mma_f16_elect(d0 + (jj & 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kStage16 + 2 * k),
+                                                     kDescHi | (uint64_t)(x_lo + (jj >> 1) * kChunk16 + 2 * k), idesc,
+                                                     (jj < 2 && k == 0) ? 0u : 1u);
+                                }
                                 tr.log('M', tl, s, t * 64 + jj);
                                 tc_commit_elect(bar_empty + 8 * slot);
-                                if (jj == 7 && sop.n_loads == 8) { tc_commit_elect(bar_acc + 8 * t); tr.log('C', tl, s, t); }
                             }
+#pragma unroll
+                            for (int q = 0; q < RING; ++q) used[q] += 2;
+                            if (sop.n_loads == 8) { tc_commit_elect(bar_acc + 8 * t); tr.log('C', tl, s, t); }
                             j0 = 8;
                         }
-                        for (int j = j0; j < sop.n_loads; ++j, ++it) {
+                        for (int j = j0; j < sop.n_loads; ++j) {
                             const LoadOp op = a.loads[li0 + j];
-                            const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                            mbar_wait(bar_full + 8 * slot, ph);
+                            const uint32_t slot = (uint32_t)j % RING;
+                            uint32_t cnt = slot == 0 ? used[0] : slot == 1 ? used[1] : slot == 2 ? used[2] : used[3];
+                            mbar_wait(bar_full + 8 * slot, cnt & 1);
                             tc_fence_after();
+                            if (slot == 0) ++used[0]; else if (slot == 1) ++used[1]; else if (slot == 2) ++used[2]; else ++used[3];
                             tr.log('F', tl, s, t * 64 + j);
                             const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u);
-                            const uint32_t w_stride = ((uint32_t)op.bytes * 16u) / op.n_chunks;
+                            const uint32_t w_stride = op.n_chunks == 4 ? ((uint32_t)op.bytes * 4u) : ((uint32_t)op.bytes * 16u);
                             for (int c = 0; c < op.n_chunks; ++c) {
                                 const int xc = op.a_chunk + c;
                                 const uint32_t x_addr = sbase + t * TILE_SMEM + (xc < 4 ? SMEM_A + xc * A_CHUNK_BYTES : SMEM_X);
@@ -328,16 +343,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast_kernel(const __grid_co
                                 for (int k = 0; k < op.nk; ++k) {
                                     const uint32_t koff = (uint32_t)(op.k0 + k) * 32u;   // 16 f16 = 32 B inside the swizzle row
                                     tc_mma_f16_elect(tmem_base + t * 256 + op.d_col, umma_desc_sw128(a_addr + koff),
-                                               umma_desc_sw128(b_addr + koff), idesc, (op.first && c == 0 && k == 0) ? 0u : 1u);
+                                                     umma_desc_sw128(b_addr + koff), idesc, (op.first && c == 0 && k == 0) ? 0u : 1u);
                                 }
                             }
                             tr.log('M', tl, s, t * 64 + j);
                             tc_commit_elect(bar_empty + 8 * slot);      // ring stage reusable once these MMAs retire
-                            tr.log('K', tl, s, t * 64 + j);
                             if (op.last) { tc_commit_elect(bar_acc + 8 * t); tr.log('C', tl, s, t); }
                         }
                     }
-                    li0 += a.stages[s].n_loads;
+                    li0 += sop.n_loads;
                 }
             }
         }
