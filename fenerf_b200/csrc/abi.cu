@@ -105,6 +105,16 @@ int fenerf_siren_points(const fenerf_field_desc* field, const void* packed, cons
     return run_field(L, packed, points, dirs, film, batch, points_per_batch, dir_group, 0, precision, out, st);
 }
 
+int fenerf_camera_poses(int32_t n, int32_t mode, float h_stddev, float v_stddev, float h_mean, float v_mean,
+                        const float* draw_theta, const float* draw_phi, float* cam2world, float* pitch, float* yaw,
+                        void* stream) {
+    FN_REQUIRE(n >= 1 && cam2world && pitch && yaw, "bad argument");
+    FN_REQUIRE(mode >= FENERF_CAMERA_FIXED && mode <= FENERF_CAMERA_GAUSSIAN, "unsupported camera mode %d", mode);
+    FN_REQUIRE(mode == FENERF_CAMERA_FIXED || (draw_theta && draw_phi), "camera mode %d needs the two random draws", mode);
+    return camera_poses(n, mode, h_stddev, v_stddev, h_mean, v_mean, draw_theta, draw_phi, cam2world, pitch, yaw,
+                        (cudaStream_t)stream);
+}
+
 int fenerf_ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_lin, const float* z_lin,
                      const float* cam2world, const float* rng_perturb, float* points, float* z_vals, float* dirs,
                      float* origins, void* stream) {
@@ -176,7 +186,7 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
     if (int e = run_field(L, packed, points_c, dirs, film, rd->batch, ppb, rd->num_steps, rd->lock_view_dependence,
                           rd->precision, raw_c, st)) return e;
     if (rd->precision == FENERF_PRECISION_GUARD) {
-        float tau = rd->guard_tau > 0.f ? rd->guard_tau : 4e-3f;
+        float tau = rd->guard_tau > 0.f ? rd->guard_tau : 1.5e-3f;
         if (int e = guard_refine(L, (const unsigned char*)packed, points_c, dirs, film, rd->batch, rays, rd->num_steps,
                                  rd->lock_view_dependence, tau, raw_c, guard, st)) return e;
     }

@@ -71,7 +71,65 @@ ray_setup_kernel(int B, int H, int W, int S, float tan_half, const float* __rest
     }
 }
 
+// Camera pose -> 4x4 camera-to-world, one thread per image.  Same operation order as
+// sample_camera_positions + create_cam2world_matrix (volumetric_rendering.py:179-248) after the
+// random draws: theta = draw * stddev + mean (or the uniform / fixed variants), phi clamped to
+// [1e-5, pi - 1e-5], origin on the unit sphere, look-at with up = (0, 1, 0).
+__global__ void camera_kernel(int n, int mode, float h_std, float v_std, float h_mean, float v_mean,
+                              const float* __restrict__ draw_theta, const float* __restrict__ draw_phi,
+                              float* __restrict__ c2w, float* __restrict__ pitch, float* __restrict__ yaw) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    float theta, phi;
+    if (mode == 1) {            // uniform: (u - 0.5) * 2 * stddev + mean
+        theta = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(draw_theta[b], 0.5f), 2.f), h_std), h_mean);
+        phi = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(draw_phi[b], 0.5f), 2.f), v_std), v_mean);
+    } else if (mode == 2) {     // normal / gaussian: z * stddev + mean
+        theta = __fadd_rn(__fmul_rn(draw_theta[b], h_std), h_mean);
+        phi = __fadd_rn(__fmul_rn(draw_phi[b], v_std), v_mean);
+    } else {                    // fixed pose
+        theta = h_mean;
+        phi = v_mean;
+    }
+    phi = fminf(fmaxf(phi, 1e-5f), 3.14159265358979323846f - 1e-5f);
+    const float sp = sinf(phi), cp = cosf(phi), st = sinf(theta), ct = cosf(theta);
+    const float o[3] = {__fmul_rn(sp, ct), cp, __fmul_rn(sp, st)};
+    auto normalize = [](float (&v)[3]) {
+        float n2 = __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2]));
+        float nn = sqrtf(n2);
+        v[0] = __fdiv_rn(v[0], nn); v[1] = __fdiv_rn(v[1], nn); v[2] = __fdiv_rn(v[2], nn);
+    };
+    float f[3] = {-o[0], -o[1], -o[2]};
+    normalize(f);      // forward_vector = normalize_vecs(-camera_origin)
+    normalize(f);      // create_cam2world_matrix normalises it again
+    // left = normalize(cross(up, f)), up = (0, 1, 0)
+    float l[3] = {__fsub_rn(__fmul_rn(1.f, f[2]), __fmul_rn(0.f, f[1])), __fsub_rn(__fmul_rn(0.f, f[0]), __fmul_rn(0.f, f[2])),
+                  __fsub_rn(__fmul_rn(0.f, f[1]), __fmul_rn(1.f, f[0]))};
+    normalize(l);
+    float u[3] = {__fsub_rn(__fmul_rn(f[1], l[2]), __fmul_rn(f[2], l[1])), __fsub_rn(__fmul_rn(f[2], l[0]), __fmul_rn(f[0], l[2])),
+                  __fsub_rn(__fmul_rn(f[0], l[1]), __fmul_rn(f[1], l[0]))};
+    normalize(u);
+    float* M = c2w + (size_t)b * 16;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        M[i * 4 + 0] = -l[i];
+        M[i * 4 + 1] = u[i];
+        M[i * 4 + 2] = -f[i];
+        M[i * 4 + 3] = o[i];
+    }
+    M[12] = 0.f; M[13] = 0.f; M[14] = 0.f; M[15] = 1.f;
+    pitch[b] = phi;
+    yaw[b] = theta;
+}
+
 }  // namespace
+
+int camera_poses(int n, int mode, float h_std, float v_std, float h_mean, float v_mean, const float* draw_theta,
+                 const float* draw_phi, float* c2w, float* pitch, float* yaw, cudaStream_t st) {
+    camera_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, mode, h_std, v_std, h_mean, v_mean, draw_theta, draw_phi, c2w, pitch, yaw);
+    FN_LAUNCH_OK("camera_kernel");
+    return 0;
+}
 
 int ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_lin, const float* z_lin,
               const float* cam2world, const float* rng_perturb, float* points, float* z_vals, float* dirs,

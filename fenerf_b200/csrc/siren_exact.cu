@@ -22,7 +22,6 @@ namespace fn {
 
 namespace {
 
-constexpr int TM = 64;           // points per tile
 constexpr int KA = 304;          // 256 + max padded extras (3 + 32 -> 48)
 constexpr int KC = 16;           // weight rows per pipeline slab
 constexpr int NTHREADS = 256;
@@ -44,7 +43,11 @@ struct ExactArgs {
     int lock_dirs;
 };
 
+// P = points per thread (4: dense 64-point tiles; 1: 16-point tiles for the sparse GUARD gather, where
+// a tile's latency matters more than FMA efficiency)
+template <int P>
 struct Smem {
+    static constexpr int TM = 16 * P;
     float A[KA][TM];
     float W[2][KC][FN_H];
     float pos[3][TM];
@@ -69,8 +72,9 @@ __device__ __forceinline__ void load_slab(float (*dst)[FN_H], const float* src, 
     }
 }
 
-// acc[m][j*4+i] += sum_k A[k][tm*4+m] * Wt[k][tn*4 + j*64 + i]   for k in [0, K)
-__device__ __forceinline__ void gemm_tile(Smem& s, const float* __restrict__ wt, int K, float (&acc)[4][16], int tid) {
+// acc[m][j*4+i] += sum_k A[k][tm*P+m] * Wt[k][tn*4 + j*64 + i]   for k in [0, K)
+template <int P>
+__device__ __forceinline__ void gemm_tile(Smem<P>& s, const float* __restrict__ wt, int K, float (&acc)[P][16], int tid) {
     const int tn = tid & 15, tm = tid >> 4;
     const int nslab = K / KC;
     load_slab(s.W[0], wt, tid);
@@ -87,14 +91,20 @@ __device__ __forceinline__ void gemm_tile(Smem& s, const float* __restrict__ wt,
         const float(*W)[FN_H] = s.W[c & 1];
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&s.A[c * KC + kk][tm * 4]);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            float av[P];
+            if constexpr (P == 4) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&s.A[c * KC + kk][tm * 4]);
+                av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+            } else {
+#pragma unroll
+                for (int m = 0; m < P; ++m) av[m] = s.A[c * KC + kk][tm * P + m];
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 w4 = *reinterpret_cast<const float4*>(&W[kk][tn * 4 + j * 64]);
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                for (int m = 0; m < 4; ++m)
+                for (int m = 0; m < P; ++m)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) acc[m][j * 4 + i] = fmaf(av[m], wv[i], acc[m][j * 4 + i]);
             }
@@ -105,30 +115,29 @@ __device__ __forceinline__ void gemm_tile(Smem& s, const float* __restrict__ wt,
 
 // A[col][pt] = sin(freq * acc + phase), per-point FiLM rows (points of a tile may belong to
 // different batch elements in gather mode)
-__device__ __forceinline__ void film_store(Smem& s, const float* __restrict__ film, int n_film, int layer,
-                                           float (&acc)[4][16], int tid) {
+template <int P>
+__device__ __forceinline__ void film_store(Smem<P>& s, const float* __restrict__ film, int n_film, int layer,
+                                           float (&acc)[P][16], int tid) {
     const int tn = tid & 15, tm = tid >> 4;
-    const float* fl[4];
+    const float* fl[P];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) fl[m] = film + ((size_t)s.bidx[tm * 4 + m] * n_film + layer) * 2 * FN_H;
+    for (int m = 0; m < P; ++m) fl[m] = film + ((size_t)s.bidx[tm * P + m] * n_film + layer) * 2 * FN_H;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int col = tn * 4 + j * 64 + i;
-            float4 v;
-            float* vp = &v.x;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < P; ++m) {
                 float fr = __ldg(fl[m] + col), ph = __ldg(fl[m] + FN_H + col);
                 // torch: sin(freq * x + phase_shift), mul and add rounded separately (siren.py:123)
-                vp[m] = sinf(__fadd_rn(__fmul_rn(fr, acc[m][j * 4 + i]), ph));
+                s.A[col][tm * P + m] = sinf(__fadd_rn(__fmul_rn(fr, acc[m][j * 4 + i]), ph));
             }
-            *reinterpret_cast<float4*>(&s.A[col][tm * 4]) = v;
         }
 }
 
-__device__ __forceinline__ void init_bias(const float* __restrict__ bias, float (&acc)[4][16], int tid) {
+template <int P>
+__device__ __forceinline__ void init_bias(const float* __restrict__ bias, float (&acc)[P][16], int tid) {
     const int tn = tid & 15;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -136,7 +145,7 @@ __device__ __forceinline__ void init_bias(const float* __restrict__ bias, float 
         for (int i = 0; i < 4; ++i) {
             float b = __ldg(bias + tn * 4 + j * 64 + i);
 #pragma unroll
-            for (int m = 0; m < 4; ++m) acc[m][j * 4 + i] = b;
+            for (int m = 0; m < P; ++m) acc[m][j * 4 + i] = b;
         }
 }
 
@@ -172,10 +181,11 @@ __device__ __forceinline__ float grid_feature(const float* __restrict__ grid, in
     return out;
 }
 
-template <bool kGather>
+template <bool kGather, int P>
 __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
+    constexpr int TM = 16 * P;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    Smem<P>& s = *reinterpret_cast<Smem<P>*>(smem_raw);
     const int tid = threadIdx.x;
     const FnLayout& L = a.L;
     const unsigned char* pk = a.packed;
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
                 s.A[FN_H + 3 + ch][pt] = grid_feature(grid, L.grid_res, G, s.pos[0][pt], s.pos[1][pt], s.pos[2][pt], ch);
             }
         }
-        float acc[4][16];
+        float acc[P][16];
         const int tn = tid & 15, tm = tid >> 4;
         // ---- first layer: 3 -> 256 ----
         {
@@ -236,16 +246,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
             init_bias(reinterpret_cast<const float*>(pk + L.first_b), acc, tid);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                float av[4];
+                float av[P];
 #pragma unroll
-                for (int m = 0; m < 4; ++m) av[m] = s.pos[k][tm * 4 + m];
+                for (int m = 0; m < P; ++m) av[m] = s.pos[k][tm * P + m];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float w = __ldg(wt + k * FN_H + tn * 4 + j * 64 + i);
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) acc[m][j * 4 + i] = fmaf(av[m], w, acc[m][j * 4 + i]);
+                        for (int m = 0; m < P; ++m) acc[m][j * 4 + i] = fmaf(av[m], w, acc[m][j * 4 + i]);
                     }
             }
             __syncthreads();   // grid features / pos reads done before A rows < 256 are written
@@ -295,7 +305,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
 int siren_points_exact(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs,
                        const int32_t* only_idx, int n_only, float* out, cudaStream_t st) {
-    static_assert(sizeof(Smem) <= 113 * 1024, "two CTAs per SM must fit");
+    static_assert(sizeof(Smem<4>) <= 113 * 1024, "two CTAs per SM must fit");
+    constexpr int TM = 64;
     ExactArgs a;
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.only_idx = only_idx; a.out = out;
     a.n_only_dev = nullptr;
@@ -306,14 +317,14 @@ int siren_points_exact(const FnLayout& L, const unsigned char* packed, const flo
     if (a.n_items <= 0) return 0;
     FN_REQUIRE(L.kx_pad <= KA - FN_H, "extra colour inputs (%d) exceed the tile", L.kx_pad);
     FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);
-    size_t smem = sizeof(Smem);
+    size_t smem = sizeof(Smem<4>);
     int blocks = (int)(a.n_items < (long long)num_sms() * 2 ? a.n_items : (long long)num_sms() * 2);
     if (gather) {
-        FN_CUDA_OK(cudaFuncSetAttribute(siren_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        siren_exact_kernel<true><<<blocks, NTHREADS, smem, st>>>(a);
+        FN_CUDA_OK(cudaFuncSetAttribute(siren_exact_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        siren_exact_kernel<true, 4><<<blocks, NTHREADS, smem, st>>>(a);
     } else {
-        FN_CUDA_OK(cudaFuncSetAttribute(siren_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        siren_exact_kernel<false><<<blocks, NTHREADS, smem, st>>>(a);
+        FN_CUDA_OK(cudaFuncSetAttribute(siren_exact_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        siren_exact_kernel<false, 4><<<blocks, NTHREADS, smem, st>>>(a);
     }
     FN_LAUNCH_OK("siren_exact_kernel");
     return 0;
@@ -356,9 +367,11 @@ int guard_refine(const FnLayout& L, const unsigned char* packed, const float* po
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = raw;
     a.only_idx = scratch_idx + 1; a.n_only_dev = scratch_idx; a.n_only = 0; a.n_items = 0;
     a.ppb = rays_per_batch * num_steps; a.tiles_per_batch = 1; a.dir_group = num_steps; a.lock_dirs = lock_dirs;
-    size_t smem = sizeof(Smem);
-    FN_CUDA_OK(cudaFuncSetAttribute(siren_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    siren_exact_kernel<true><<<num_sms() * 2, NTHREADS, smem, st>>>(a);
+    // 16-point tiles: the guard list is a few thousand points at most, so spread it over every SM and
+    // keep each tile's latency low (one wave of 64-point tiles idles most of the chip for ~0.3 ms)
+    size_t smem = sizeof(Smem<1>);
+    FN_CUDA_OK(cudaFuncSetAttribute(siren_exact_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    siren_exact_kernel<true, 1><<<num_sms() * 4, NTHREADS, smem, st>>>(a);
     FN_LAUNCH_OK("siren_exact_kernel(guard)");
     return 0;
 }

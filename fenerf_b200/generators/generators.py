@@ -27,18 +27,24 @@ class _RenderSkeleton:
     def _render(self, film, batch_size, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean,
                 v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs, staged):
         device = torch.device(self.device)
+        if device.type != 'cuda':
+            raise RuntimeError("fenerf_b200 renders on CUDA only; move the generator to a B200 (got %s)" % device)
         rng = kwargs.get('_rng') or vr.DeviceRng(device)
         n_rays = img_size * img_size
         n_samples = num_steps * 2 if hierarchical_sample else num_steps
         with torch.no_grad():
             # draw #1, then the camera draws (transform_sampled_points, volumetric_rendering.py:147-153)
             rng_perturb = rng.rand(batch_size, n_rays, num_steps, 1)
-            camera_origin, pitch, yaw = vr.sample_camera_positions(
-                n=batch_size, r=1, horizontal_stddev=h_stddev, vertical_stddev=v_stddev, horizontal_mean=h_mean,
-                vertical_mean=v_mean, device=device, mode=sample_dist, rng=rng)
-            forward_vector = vr.normalize_vecs(-camera_origin)
-            cam2world = vr.create_cam2world_matrix(forward_vector, camera_origin, device=device).contiguous()
-            x_lin, y_lin, z_lin = vr.ray_tables(img_size, num_steps, ray_start, ray_end, device)
+            fused = ops.camera_poses(batch_size, sample_dist, h_stddev, v_stddev, h_mean, v_mean, rng, device)
+            if fused is not None:
+                cam2world, pitch, yaw = fused
+            else:   # rare camera modes: the torch helpers (same draw order)
+                camera_origin, pitch, yaw = vr.sample_camera_positions(
+                    n=batch_size, r=1, horizontal_stddev=h_stddev, vertical_stddev=v_stddev, horizontal_mean=h_mean,
+                    vertical_mean=v_mean, device=device, mode=sample_dist, rng=rng)
+                forward_vector = vr.normalize_vecs(-camera_origin)
+                cam2world = vr.create_cam2world_matrix(forward_vector, camera_origin, device=device).contiguous()
+            x_lin, y_lin, z_lin = ops.ray_tables(img_size, num_steps, ray_start, ray_end, device)
             rng_noise_c = rng_u = None
             if hierarchical_sample:
                 clamp_mode, noise_std = kwargs['clamp_mode'], kwargs['nerf_noise']

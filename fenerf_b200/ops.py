@@ -134,6 +134,46 @@ def needs_grad(module, *tensors):
 # --------------------------------------------------------------------------------------------
 # render stages (exposed for stage-level parity tests and for callers that bring their own rays)
 # --------------------------------------------------------------------------------------------
+def camera_poses(n, mode, h_stddev, v_stddev, h_mean, v_mean, rng, device):
+    """Fused camera pose sampling + look-at matrix (one launch instead of ~45 tiny torch kernels).
+    Draw order as the reference: theta then phi.  Returns (cam2world (n,4,4), pitch (n,1), yaw (n,1)),
+    or None when `mode` is one the fused kernel does not cover (caller falls back to the torch helpers)."""
+    if mode not in _lib.CAMERA_MODE and mode in ("hybrid", "truncated_gaussian", "spherical_uniform"):
+        return None
+    code = _lib.CAMERA_MODE.get(mode, 0)
+    d_theta = d_phi = None
+    if code == 1:
+        d_theta, d_phi = rng.rand(n, 1), rng.rand(n, 1)
+    elif code == 2:
+        d_theta, d_phi = rng.randn(n, 1), rng.randn(n, 1)
+    c2w = torch.empty((n, 4, 4), dtype=torch.float32, device=device)
+    pitch = torch.empty((n, 1), dtype=torch.float32, device=device)
+    yaw = torch.empty((n, 1), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().fenerf_camera_poses(
+            n, code, float(h_stddev), float(v_stddev), float(h_mean), float(v_mean),
+            _chk(d_theta.contiguous(), "draw_theta", device) if d_theta is not None else 0,
+            _chk(d_phi.contiguous(), "draw_phi", device) if d_phi is not None else 0,
+            c2w.data_ptr(), pitch.data_ptr(), yaw.data_ptr(), _stream(device)))
+    return c2w, pitch, yaw
+
+
+_TABLES = {}
+
+
+def ray_tables(img_size, num_steps, ray_start, ray_end, device):
+    """Cached linspace tables (torch.linspace, so the values are the reference's to the bit)."""
+    key = (img_size, num_steps, float(ray_start), float(ray_end), str(device))
+    t = _TABLES.get(key)
+    if t is None:
+        from .generators import volumetric_rendering as vr
+        t = vr.ray_tables(img_size, num_steps, ray_start, ray_end, device)
+        if len(_TABLES) > 64:
+            _TABLES.clear()
+        _TABLES[key] = t
+    return t
+
+
 def ray_setup(rd, x_lin, y_lin, z_lin, cam2world, rng_perturb):
     device = cam2world.device
     b, n, s = rd.batch, rd.img_h * rd.img_w, rd.num_steps

@@ -146,8 +146,23 @@ typedef struct fenerf_render_desc {
     int32_t precision;          /* FENERF_PRECISION_* */
     float   noise_std;          /* nerf_noise */
     float   tan_half_fov;       /* (float) tan(2*pi*fov/360 / 2), volumetric_rendering.py:119 */
-    float   guard_tau;          /* GUARD threshold on |sigma_far| (default 4e-3 if <= 0) */
+    float   guard_tau;          /* GUARD threshold on |sigma_far| (default 1.5e-3 if <= 0: 5x the fp16 path's
+                                   measured 3e-4 max sigma error, profiles/r01_field_fast_vs_exact*.log) */
 } fenerf_render_desc;
+
+/* Camera pose sampling after the random draws, and the look-at camera-to-world matrix.
+ * Replaces the arithmetic of sample_camera_positions + create_cam2world_matrix
+ * (generators/volumetric_rendering.py:179-248) for the modes the named curricula use; the caller
+ * makes the draws (torch.rand / torch.randn (n,1), theta first) so the RNG stream is the reference's.
+ *   mode FIXED: theta = h_mean, phi = v_mean (draws may be NULL)
+ *   mode UNIFORM: (draw - 0.5) * 2 * stddev + mean;  mode GAUSSIAN: draw * stddev + mean
+ * out: cam2world (n,16) row-major; pitch (n) = clamped phi; yaw (n) = theta                        */
+#define FENERF_CAMERA_FIXED 0
+#define FENERF_CAMERA_UNIFORM 1
+#define FENERF_CAMERA_GAUSSIAN 2
+int fenerf_camera_poses(int32_t n, int32_t mode, float h_stddev, float v_stddev, float h_mean, float v_mean,
+                        const float* draw_theta, const float* draw_phi, float* cam2world, float* pitch, float* yaw,
+                        void* stream);
 
 /* Camera rays, stratified perturbation and camera-to-world transform.
  * Replaces get_initial_rays_trig + perturb_points + the three bmm of transform_sampled_points
