@@ -16,6 +16,7 @@
 //                       the first colour layer's extra inputs dir(3), grid_feat(G), zero pad
 //   Wbuf [2][16][256]   double-buffered 16-row slabs of the k-major weights via cp.async
 //   each thread owns a 4-point x 16-column micro tile; 5 LDS.128 feed 64 FFMA per k
+//   (the 16-point gather variant maps lanes point-major so a warp's weight reads broadcast)
 #include "common.cuh"
 
 namespace fn {
@@ -48,8 +49,11 @@ struct ExactArgs {
 template <int P>
 struct Smem {
     static constexpr int TM = 16 * P;
+    // weight-slab pipeline depth: 2 for the dense tiles (two CTAs per SM must fit), 6 for the small
+    // gather tiles whose 256 FFMA per slab cannot hide an L2 round trip behind a single prefetch
+    static constexpr int NS = P == 4 ? 2 : 6;
     float A[KA][TM];
-    float W[2][KC][FN_H];
+    float W[NS][KC][FN_H];
     float pos[3][TM];
     long long flat[TM];   // b * ppb + p of each tile slot, -1 if the slot is empty
     int bidx[TM];
@@ -75,20 +79,20 @@ __device__ __forceinline__ void load_slab(float (*dst)[FN_H], const float* src, 
 // acc[m][j*4+i] += sum_k A[k][tm*P+m] * Wt[k][tn*4 + j*64 + i]   for k in [0, K)
 template <int P>
 __device__ __forceinline__ void gemm_tile(Smem<P>& s, const float* __restrict__ wt, int K, float (&acc)[P][16], int tid) {
-    const int tn = tid & 15, tm = tid >> 4;
+    const int tn = P == 4 ? (tid & 15) : (tid >> 4), tm = P == 4 ? (tid >> 4) : (tid & 15);
     const int nslab = K / KC;
-    load_slab(s.W[0], wt, tid);
-    cp_async_commit();
+    constexpr int NS = Smem<P>::NS;
+#pragma unroll
+    for (int st = 0; st < NS - 1; ++st) {
+        if (st < nslab) load_slab(s.W[st], wt + (size_t)st * KC * FN_H, tid);
+        cp_async_commit();
+    }
     for (int c = 0; c < nslab; ++c) {
-        if (c + 1 < nslab) {
-            load_slab(s.W[(c + 1) & 1], wt + (size_t)(c + 1) * KC * FN_H, tid);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        const float(*W)[FN_H] = s.W[c & 1];
+        cp_async_wait<NS - 2>();       // slab c has landed (one group per slab, NS-1 in flight)
+        __syncthreads();               // ... for every thread, and slab c-1's buffer is free again
+        if (c + NS - 1 < nslab) load_slab(s.W[(c + NS - 1) % NS], wt + (size_t)(c + NS - 1) * KC * FN_H, tid);
+        cp_async_commit();
+        const float(*W)[FN_H] = s.W[c % NS];
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
             float av[P];
@@ -109,8 +113,9 @@ __device__ __forceinline__ void gemm_tile(Smem<P>& s, const float* __restrict__ 
                     for (int i = 0; i < 4; ++i) acc[m][j * 4 + i] = fmaf(av[m], wv[i], acc[m][j * 4 + i]);
             }
         }
-        __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();                   // all reads of A and W done before the caller overwrites A
 }
 
 // A[col][pt] = sin(freq * acc + phase), per-point FiLM rows (points of a tile may belong to
@@ -118,7 +123,7 @@ __device__ __forceinline__ void gemm_tile(Smem<P>& s, const float* __restrict__ 
 template <int P>
 __device__ __forceinline__ void film_store(Smem<P>& s, const float* __restrict__ film, int n_film, int layer,
                                            float (&acc)[P][16], int tid) {
-    const int tn = tid & 15, tm = tid >> 4;
+    const int tn = P == 4 ? (tid & 15) : (tid >> 4), tm = P == 4 ? (tid >> 4) : (tid & 15);
     const float* fl[P];
 #pragma unroll
     for (int m = 0; m < P; ++m) fl[m] = film + ((size_t)s.bidx[tm * P + m] * n_film + layer) * 2 * FN_H;
@@ -138,7 +143,7 @@ __device__ __forceinline__ void film_store(Smem<P>& s, const float* __restrict__
 
 template <int P>
 __device__ __forceinline__ void init_bias(const float* __restrict__ bias, float (&acc)[P][16], int tid) {
-    const int tn = tid & 15;
+    const int tn = P == 4 ? (tid & 15) : (tid >> 4);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
             }
         }
         float acc[P][16];
-        const int tn = tid & 15, tm = tid >> 4;
+        const int tn = P == 4 ? (tid & 15) : (tid >> 4), tm = P == 4 ? (tid >> 4) : (tid & 15);
         // ---- first layer: 3 -> 256 ----
         {
             const float* wt = reinterpret_cast<const float*>(pk + L.first_w);
