@@ -2,6 +2,7 @@
 // dispatch and the five-launch render pipeline.  No torch types, no allocation, no global state
 // beyond the thread-local error string and the launch counter.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fn {
 thread_local char g_err[512] = "";
@@ -54,6 +55,12 @@ int run_field(const FnLayout& L, const void* packed, const float* points, const 
     const unsigned char* pk = static_cast<const unsigned char*>(packed);
     if (precision == FENERF_PRECISION_EXACT)
         return siren_points_exact(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, nullptr, 0, out, st);
+    // two generations of the tcgen05 kernel; FENERF_B200_FAST_KERNEL=1 selects the paired-tile one
+    static const int which = [] { const char* e = getenv("FENERF_B200_FAST_KERNEL"); return e ? atoi(e) : 1; }();
+    if (which == 3)
+        return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), st);
+    if (which == 2)
+        return siren_points_fast2(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), st);
     return siren_points_fast(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, st);
 }
 

@@ -67,6 +67,13 @@ int siren_points_fast(const FnLayout& L, const unsigned char* packed, const floa
                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
                       cudaStream_t st);
 void set_fast_trace(long long* buf);
+long long* get_fast_trace();
+int siren_points_fast2(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
+                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
+                       long long* trace, cudaStream_t st);
+int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
+                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
+                       long long* trace, cudaStream_t st);
 int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                  const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
                  float* raw, int32_t* scratch_idx, cudaStream_t st);

@@ -6,7 +6,9 @@
 //
 //   first layer      Wt0 [3][256] f32 (k-major)          b0 [256]
 //   hidden layer l   Wt  [K_l][256] f32 (k-major)        b  [256]        (exact kernel)
-//                    img [K_l/64][256 rows][64 k] f16, 128B-swizzled     (tcgen05 kernel)
+//                    img [2 halves][K_l/64][128 rows][64 k] f16, 128B-swizzled (tcgen05 kernel):
+//                        feature half h, k-chunk kc at byte h*64 KB + kc*16 KB, so one bulk copy can
+//                        bring several k-chunks of a half (32 KB = 8 MMAs of work per ring stage)
 //     l in [0, n_hidden): trunk layers 1.., then colour layers 0..;  K_l = 256 except the first
 //     colour layer, whose extra inputs are appended after the 256 x-rows:
 //        f32:  rows 256.. = dir(3), feat(G), zero pad to KX_PAD
@@ -105,4 +107,12 @@ __host__ __device__
 #endif
 static inline uint32_t fn_sw128_offset(uint32_t row, uint32_t k) {
     return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ (row & 7u)) & 7u) << 4) + (k & 7u) * 2u;
+}
+
+// Byte offset of weight element (output feature n, input k) inside a hidden layer's f16 image.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline uint32_t fn_hidden_img_offset(uint32_t n, uint32_t k) {
+    return (n >> 7) * 65536u + (k / FN_KCHUNK) * 16384u + fn_sw128_offset(n & 127u, k % FN_KCHUNK);
 }

@@ -54,10 +54,8 @@ __global__ void pack_hidden_kernel(const float* __restrict__ w, const float* __r
     // f16 image: thread (x = k within tile, y -> n rows)
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int n = n0 + i, k = k0 + threadIdx.x;
-        if (k < FN_H) {
-            unsigned char* chunk = img + (size_t)(k / FN_KCHUNK) * FN_IMG_BYTES;
-            *reinterpret_cast<__half*>(chunk + fn_sw128_offset(n, k % FN_KCHUNK)) = __float2half_rn(tile[i][threadIdx.x]);
-        }
+        if (k < FN_H)   // image order [feature half][k-chunk][128 rows][64 k]: a half's four k-chunks are contiguous
+            *reinterpret_cast<__half*>(img + fn_hidden_img_offset(n, k)) = __float2half_rn(tile[i][threadIdx.x]);
     }
     if (blockIdx.x == 0 && threadIdx.y == 0) bo[n0 + threadIdx.x] = b[n0 + threadIdx.x];
 }

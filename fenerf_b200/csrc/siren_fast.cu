@@ -45,6 +45,7 @@
 //   ring  4 x 16 KB      weight stages [128 feature rows][64 k] (half of one k-chunk image)
 #include "common.cuh"
 #include "siren_common.cuh"
+#include "tc5.cuh"
 
 namespace fn {
 
@@ -103,112 +104,7 @@ struct FastArgs {
     long long* trace;   // diagnostics: per-role clock64 log of CTA 0 (fenerf_debug_trace), or NULL
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = 0;
-    for (uint32_t spin = 0;; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-        if (spin == 64) t0 = clock64();
-        if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// Warp-converged variants: every lane executes the call with identical (warp-uniform) operands and
-// one elected lane issues.  Keeps the issuer loop out of divergent code, so operands stay in uniform
-// registers instead of being re-broadcast (R2UR + ELECT loop) around every instruction.
-__device__ __forceinline__ void tc_mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
-                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO),
-// LBO unused for swizzled K-major, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
-    d |= 1ull << 46;
-    d |= 2ull << 61;
-    return d;
-}
-// the constant upper word of umma_desc_sw128: SBO 1024 B, version 1, SWIZZLE_128B
-constexpr uint64_t kDescHi = ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-// instruction descriptor, kind::f16: D f32, A/B f16, both K-major, M = 128
-__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t n) {
-    return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
-    hi = __float2half_rn(v);
-    lo = __float2half_rn(v - __half2float(hi));
-}
-
-// Diagnostics: CTA 0 logs (tag, clock64) pairs for its first tiles; one 4096-entry lane per role.
-template <bool kOn>
-struct Tracer {
-    long long* p; int n;
-    __device__ Tracer(long long* base, int role) : p(kOn && base && blockIdx.x == 0 ? base + role * 4096 : nullptr), n(0) {}
-    __device__ __forceinline__ void log(int kind, int tile, int stage, int item) {
-        if (kOn && p && tile < 2 && n < 2040) { p[2 + 2 * n] = ((long long)kind << 48) | ((long long)tile << 32) | (stage << 16) | item; p[3 + 2 * n] = clock64(); ++n; p[0] = n; }
-    }
-};
+using namespace tc5;
 
 // ---- the kernel -----------------------------------------------------------------------------
 template <bool kTrace>
@@ -532,7 +428,7 @@ void push_image_loads(FastArgs& A, size_t img_off, int n_chunks, bool first_of_s
     for (int kc = 0; kc < n_chunks; ++kc)
         for (int half = 0; half < 2; ++half) {
             LoadOp& op = A.loads[A.n_loads++];
-            op.src = (uint32_t)(img_off + (size_t)kc * FN_IMG_BYTES + (size_t)half * STAGE_BYTES);
+            op.src = (uint32_t)(img_off + (size_t)half * 65536 + (size_t)kc * STAGE_BYTES);   // [half][kc][128 rows]
             op.bytes = STAGE_BYTES / 16;
             op.a_chunk = (uint8_t)kc;
             op.k0 = 0; op.nk = 4; op.n8 = TILE / 8; op.d_col = (uint16_t)(half * 128);
@@ -603,6 +499,7 @@ long long* g_trace = nullptr;
 }  // namespace
 
 void set_fast_trace(long long* buf) { g_trace = buf; }
+long long* get_fast_trace() { return g_trace; }
 
 int siren_points_fast(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,

@@ -1,0 +1,521 @@
+// Point network, FAST mode, third-generation kernel: two anti-phased tiles, three 32 KB ring slots.
+//
+// Same math as siren_fast.cu / siren_fast2.cu.  What the measurements of round 1 say
+// (profiles/r01_*.txt): per 128-point layer-tile the tensor pipe, the MUFU pipe
+// and the TMEM->register path each need ~2048 cycles, a layer is a dependency chain
+// MMA -> epilogue -> MMA, a ring slot's turnaround is ~1800 cycles whatever its size, and the MMA
+// issuer pays ~400 cycles of barrier/commit bookkeeping per ring round.  Hence:
+//   * TWO tiles per CTA (one CTA per SM) run the same layer program half a layer apart, so one
+//     tile's epilogue (MUFU + TMEM reads) overlaps the other tile's MMA phase;
+//   * ring slots are 32 KB = two k-chunks of one feature half = 8 MMAs = 512 tensor cycles per
+//     barrier round; three slots (96 KB in flight) keep one 32 KB load arriving every ~600 cycles;
+//   * that ring only fits because the per-tile 16 KB input chunk is gone: the position slots of the
+//     first layer live in activation chunk 3 (free at tile start), and the view-direction / grid
+//     feature slots of the first colour layer are written into activation chunk 0 AFTER that layer's
+//     main MMAs have retired (one extra barrier round trip per tile);
+//   * activations are MN-major (points contiguous), so the feature-per-thread epilogue stores 16
+//     bytes at a time; TMEM is drained in 16-column double-buffered pieces.
+//
+//   warps 0..2    weight producers (one per ring slot)
+//   warp  3       MMA issuer (warp-converged, elect.sync)
+//   warps 4..7    epilogue of tile X      warps 8..11   epilogue of tile Y
+#include "common.cuh"
+#include "siren_common.cuh"
+#include "tc5.cuh"
+
+namespace fn {
+
+namespace {
+
+using namespace tc5;
+
+constexpr int TILE = 128;
+constexpr int RING = 3;
+constexpr int MMA_WARP = RING;
+constexpr int EPI_WARP0 = RING + 1;
+constexpr int NTHREADS = (EPI_WARP0 + 8) * 32;      // 384
+constexpr uint32_t CHUNK_BYTES = 16384;
+constexpr uint32_t STAGE_BYTES = 32768;
+constexpr uint32_t TILE_SMEM = 4 * CHUNK_BYTES;      // four activation chunks per tile
+constexpr uint32_t SMEM_RING = 2 * TILE_SMEM;
+constexpr uint32_t SMEM_BAR = SMEM_RING + RING * STAGE_BYTES;   // 229376
+constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_LOADS = 96;
+constexpr int MAX_STAGES = 16;
+
+enum : uint8_t { EPI_FILM = 0, EPI_HEAD_TRUNK = 1, EPI_HEAD_RGB = 2 };
+enum : uint8_t { X_NONE = 0, X_POS = 1, X_EXTRA = 2 };   // load reads the K-major input slots instead of an activation chunk
+
+struct alignas(16) LoadOp {
+    uint32_t src;          // byte offset in the packed buffer
+    uint16_t bytes16;      // bytes / 16
+    uint8_t x_chunk;       // first activation chunk read (0..3)
+    uint8_t n_chunks;      // k-chunks in this load, `bytes / n_chunks` apart in the slot
+    uint8_t k0, nk;        // K-steps inside a 64-wide chunk
+    uint8_t n8;            // MMA N / 8
+    uint8_t half;          // accumulator half; for X loads: both halves (weights at 16 KB stride), half ignored
+    uint8_t first;         // 1: the first MMA of this load overwrites the accumulator
+    uint8_t w_is_a;        // 1: weights are the A operand (transposed FiLM layer); 0: B (head)
+    uint8_t xkind;         // X_*
+    uint8_t pad;
+};
+static_assert(sizeof(LoadOp) == 16, "LoadOp is 16 bytes");
+
+struct StageOp {
+    uint8_t epi;           // EPI_*
+    uint8_t film;          // FiLM layer index
+    uint8_t n_loads;
+    uint8_t uniform;       // 1: plain 256x256 FiLM layer = 4 loads (h0 k01, h0 k23, h1 k01, h1 k23)
+    uint8_t xsync;         // index of the X_EXTRA load: before it the issuer commits `xmain` and waits `xready`
+    uint8_t pad[3];
+};
+
+struct Fast3Args {
+    LoadOp loads[MAX_LOADS];
+    StageOp stages[MAX_STAGES];
+    int n_loads, n_stages;
+    FnLayout L;
+    const unsigned char* packed;
+    const float* points;
+    const float* dirs;
+    const float* film;
+    float* out;
+    long long ppb, tiles_per_batch, n_tiles;
+    int dir_group, lock_dirs;
+    long long* trace;
+};
+
+template <bool kTrace>
+__global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_constant__ Fast3Args a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + SMEM_BAR;             // [RING]
+    const uint32_t bar_empty = bar_full + 8 * RING;         // [RING]
+    const uint32_t bar_acc = bar_empty + 8 * RING;          // [2] accumulator of tile t complete (issuer -> epilogue t)
+    const uint32_t bar_aready = bar_acc + 16;               // [2] operand written + accumulator drained (epilogue t -> issuer)
+    const uint32_t bar_xmain = bar_aready + 16;             // [2] colour layer 0: main MMAs retired, chunk 0 reusable
+    const uint32_t bar_xready = bar_xmain + 16;             // [2] colour layer 0: extra input slots written into chunk 0
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * RING + 8));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar_acc + 8 * t, 1);
+            mbar_init(bar_aready + 8 * t, 4);
+            mbar_init(bar_xmain + 8 * t, 1);
+            mbar_init(bar_xready + 8 * t, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const FnLayout& L = a.L;
+
+    if (warp < RING) {
+        // ================= weight producers: load j of a (stage, tile) job -> slot j % RING = warp j % RING
+        if (lane == 0) {
+            uint32_t uses = 0;
+            for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x) {
+                const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
+                int li = 0;
+                for (int s = 0; s < a.n_stages; ++s) {
+                    const int n = a.stages[s].n_loads;
+                    for (int t = 0; t < nt; ++t)
+                        for (int j = warp; j < n; j += RING, ++uses) {
+                            mbar_wait(bar_empty + 8 * warp, (uses & 1) ^ 1);
+                            const uint32_t bytes = (uint32_t)a.loads[li + j].bytes16 * 16u;
+                            mbar_arrive_expect_tx(bar_full + 8 * warp, bytes);
+                            bulk_g2s(sbase + SMEM_RING + warp * STAGE_BYTES, a.packed + a.loads[li + j].src, bytes, bar_full + 8 * warp);
+                        }
+                    li += n;
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ================= MMA issuer (warp-converged; an elected lane issues) =================
+        uint32_t used[RING] = {0, 0, 0};
+        uint32_t n_ready[2] = {0, 0}, n_x[2] = {0, 0};
+        Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, 1);
+        const uint32_t ring_lo = (sbase + SMEM_RING) >> 4;
+        int tl = 0;
+        for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x, ++tl) {
+            const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
+            int li = 0;
+            for (int s = 0; s < a.n_stages; ++s) {
+                const StageOp sop = a.stages[s];
+                for (int t = 0; t < nt; ++t) {
+                    mbar_wait(bar_aready + 8 * t, n_ready[t] & 1);
+                    ++n_ready[t];
+                    tc_fence_after();
+                    tr.log('A', tl, s, t);
+                    const uint32_t x_lo0 = (sbase + t * TILE_SMEM) >> 4;      // activation chunk 0 of this tile
+                    const uint32_t d0 = tmem_base + (uint32_t)t * 256u;
+                    if (sop.uniform) {
+                        // straight-line: 4 rounds x 8 MMAs in ring slots 0,1,2,0: [h0 k01][h0 k23][h1 k01][h1 k23]
+                        constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);      // B (activations) MN-major
+                        constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
+                        mbar_wait(bar_full, used[0] & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int slot = jj % RING;
+                            tr.log('F', tl, s, t * 64 + jj);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (c == 1 && k == 0 && jj < 3) {   // next slot's wait overlaps this slot's MMAs
+                                        const int ns = (jj + 1) % RING;
+                                        mbar_wait(bar_full + 8 * ns, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
+                                        tc_fence_after();
+                                    }
+                                    tc_mma_f16_elect(d0 + (jj >> 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kSlot16 + c * kChunk16 + 2 * k),
+                                                     kDescHiMN | (uint64_t)(x_lo0 + ((jj & 1) * 2 + c) * kChunk16 + 256 * k), idesc,
+                                                     ((jj & 1) == 0 && c == 0 && k == 0) ? 0u : 1u);
+                                }
+                            tc_commit_elect(bar_empty + 8 * slot);
+                        }
+                        used[0] += 2; used[1] += 1; used[2] += 1;
+                    } else {
+                        for (int j = 0; j < sop.n_loads; ++j) {
+                            const LoadOp op = a.loads[li + j];
+                            if (op.xkind == X_EXTRA) {
+                                // the main MMAs of this colour layer must retire before chunk 0 is overwritten with
+                                // the extra input slots; then wait until the epilogue has written them
+                                tc_commit_elect(bar_xmain + 8 * t);
+                                mbar_wait(bar_xready + 8 * t, n_x[t] & 1);
+                                ++n_x[t];
+                                tc_fence_after();
+                                tr.log('X', tl, s, t);
+                            }
+                            const uint32_t slot = (uint32_t)j % RING;
+                            const uint32_t cnt = slot == 0 ? used[0] : slot == 1 ? used[1] : used[2];
+                            mbar_wait(bar_full + 8 * slot, cnt & 1);
+                            tc_fence_after();
+                            if (slot == 0) ++used[0]; else if (slot == 1) ++used[1]; else ++used[2];
+                            tr.log('F', tl, s, t * 64 + j);
+                            const uint32_t w_stride = ((uint32_t)op.bytes16 * 16u) / op.n_chunks;
+                            if (op.xkind != X_NONE) {
+                                // K-major input slots in chunk 3 (positions) or chunk 0 (direction / grid features);
+                                // the 32 KB slot holds the [256 features][64 slots] image: one MMA group per half
+                                const uint32_t x_lo = x_lo0 + (op.xkind == X_POS ? 3u : 0u) * (CHUNK_BYTES >> 4);
+                                const uint32_t idesc = umma_idesc_f16(TILE, 0, 0);
+#pragma unroll 1
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint32_t w_lo = ring_lo + slot * (STAGE_BYTES >> 4) + (uint32_t)h * (16384u >> 4);
+#pragma unroll 1
+                                    for (int k = 0; k < op.nk; ++k) {
+                                        const uint32_t ko = (uint32_t)(op.k0 + k) * 2u;
+                                        tc_mma_f16_elect(d0 + h * 128, kDescHi | (uint64_t)(w_lo + ko), kDescHi | (uint64_t)(x_lo + ko),
+                                                         idesc, (op.first && k == 0) ? 0u : 1u);
+                                    }
+                                }
+                            } else {
+                                const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u, op.w_is_a ? 0u : 1u, op.w_is_a ? 1u : 0u);
+                                const uint32_t d_col = d0 + (uint32_t)op.half * 128u;
+#pragma unroll 1
+                                for (int c = 0; c < op.n_chunks; ++c) {
+                                    const uint32_t x_lo = x_lo0 + (uint32_t)(op.x_chunk + c) * (CHUNK_BYTES >> 4);
+                                    const uint32_t w_lo = ring_lo + slot * (STAGE_BYTES >> 4) + ((c * w_stride) >> 4);
+#pragma unroll 4
+                                    for (int k = 0; k < op.nk; ++k) {
+                                        const uint64_t xd = kDescHiMN | (uint64_t)(x_lo + (uint32_t)(op.k0 + k) * 256u);
+                                        const uint64_t wd = kDescHi | (uint64_t)(w_lo + (uint32_t)(op.k0 + k) * 2u);
+                                        tc_mma_f16_elect(d_col, op.w_is_a ? wd : xd, op.w_is_a ? xd : wd, idesc,
+                                                         (op.first && c == 0 && k == 0) ? 0u : 1u);
+                                    }
+                                }
+                            }
+                            tc_commit_elect(bar_empty + 8 * slot);
+                        }
+                    }
+                    tc_commit_elect(bar_acc + 8 * t);
+                    tr.log('C', tl, s, t);
+                }
+                li += sop.n_loads;
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int t = (warp - EPI_WARP0) >> 2;         // which tile of the pair
+        const int q = warp & 3;                        // TMEM lane quadrant (hardware: warp id % 4)
+        const int row = q * 32 + lane;                 // feature within a half (FiLM) / point (heads, input slots)
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+        unsigned char* tsm = smem + t * TILE_SMEM;
+        const uint32_t my_acc = bar_acc + 8 * t, my_aready = bar_aready + 8 * t;
+        const uint32_t my_xmain = bar_xmain + 8 * t, my_xready = bar_xready + 8 * t;
+        const uint32_t xrow_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;   // K-major row of this point
+        const uint32_t xsw = (uint32_t)(row & 7);
+        const int C = L.out_dim;
+        const float* sigma_w = reinterpret_cast<const float*>(a.packed + L.sigma_w);
+        const float* rgb_w = reinterpret_cast<const float*>(a.packed + L.rgb_w);
+        const float* label_w = reinterpret_cast<const float*>(a.packed + L.label_w);
+        uint32_t n_acc = 0, n_x = 0;
+        Tracer<kTrace> tr((warp == EPI_WARP0 || warp == EPI_WARP0 + 4) && lane == 0 ? a.trace : nullptr, 2 + t);
+        int tl = 0;
+        for (long long pair = blockIdx.x; pair * 2 + t < a.n_tiles; pair += gridDim.x, ++tl) {
+            const long long tile = pair * 2 + t;
+            const long long b = tile / a.tiles_per_batch;
+            const long long pnt = (tile % a.tiles_per_batch) * TILE + row;
+            const bool valid = pnt < a.ppb;
+            const long long flat = b * a.ppb + pnt;
+            tr.log('T', tl, 0, 0);
+            // ---- input slots of this thread's point (layout.h): positions now (chunk 3), direction + grid
+            //      features kept in registers until the first colour layer ----
+            uint4 xslots[8];
+            {
+                float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) pos[i] = __fmul_rn(a.points[flat * 3 + i], L.input_scale);
+                    if (a.lock_dirs) dir[2] = -1.f;
+                    else {
+                        const long long di = b * (a.ppb / a.dir_group) + pnt / a.dir_group;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) dir[i] = a.dirs[di * 3 + i];
+                    }
+                }
+                __align__(16) __half slots[64];
+#pragma unroll
+                for (int i = 0; i < 64; ++i) slots[i] = __float2half_rn(0.f);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    __half hi, lo;
+                    split_f16(pos[i], hi, lo);
+                    slots[FN_SLOT_POS + i] = hi; slots[FN_SLOT_POS + 3 + i] = lo; slots[FN_SLOT_POS + 6 + i] = hi;
+                    split_f16(dir[i], hi, lo);
+                    slots[FN_SLOT_DIR + i] = hi; slots[FN_SLOT_DIR + 3 + i] = lo; slots[FN_SLOT_DIR + 6 + i] = hi;
+                }
+                if (L.grid_channels > 0 && valid) {
+                    float feat[32];
+                    grid_features32(reinterpret_cast<const float*>(a.packed + L.grid), L.grid_res, pos[0], pos[1], pos[2], feat);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) slots[FN_SLOT_FEAT + i] = __float2half_rn(feat[i]);
+                }
+                const uint4* src = reinterpret_cast<const uint4*>(slots);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xslots[j] = src[j];
+                // positions: K-step 0 = pieces 0,1 of the row, into activation chunk 3 (free at tile start)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    *reinterpret_cast<uint4*>(tsm + 3 * CHUNK_BYTES + xrow_off + (((uint32_t)j ^ xsw) << 4)) = xslots[j];
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(my_aready);
+
+            for (int s = 0; s < a.n_stages; ++s) {
+                const StageOp sop = a.stages[s];
+                const bool last = (s + 1 == a.n_stages);
+                if (sop.epi == EPI_FILM) {
+                    const int fl = row;
+                    const float* film_l = a.film + ((size_t)b * L.n_film + sop.film) * 2 * FN_H;
+                    const float* bias = reinterpret_cast<const float*>(
+                        a.packed + (sop.film == 0 ? L.first_b : L.hid_b[sop.film - 1]));
+                    float fr[2], ph[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        fr[h] = __ldg(film_l + h * 128 + fl);
+                        ph[h] = fmaf(fr[h], __ldg(bias + h * 128 + fl), __ldg(film_l + FN_H + h * 128 + fl));
+                    }
+                    if (sop.xsync) {
+                        // first colour layer: once its main MMAs have retired, chunk 0 takes the K-major extra
+                        // input slots (pieces 2..7 of the row = direction and grid features)
+                        mbar_wait(my_xmain, n_x & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int j = 2; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(tsm + xrow_off + (((uint32_t)j ^ xsw) << 4)) = xslots[j];
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(my_xready);
+                        ++n_x;
+                    }
+                    mbar_wait(my_acc, n_acc & 1);
+                    ++n_acc;
+                    tc_fence_after();
+                    tr.log('W', tl, s, 0);
+                    const uint32_t kk = (uint32_t)(fl & 63);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        // feature f = h*128 + fl -> chunk f/64, row k = f%64 of the MN-major chunk
+                        // [k/8][point/64][k%8][64 points]
+                        unsigned char* rowp = tsm + (uint32_t)(h * 2 + (fl >> 6)) * CHUNK_BYTES + (kk >> 3) * 2048u + (kk & 7u) * 128u;
+                        const uint32_t sw = kk & 7u;
+                        const float f_h = fr[h], p_h = ph[h];
+                        uint32_t r[2][16];
+                        tc_ld16(t_lane + h * 128, r[0]);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {          // 128 points: 8 groups of 16
+                            tc_wait_ld();
+                            if (g < 7) tc_ld16(t_lane + h * 128 + (g + 1) * 16, r[(g + 1) & 1]);
+#pragma unroll
+                            for (int j8 = 0; j8 < 2; ++j8) {
+                                float v[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = __sinf(fmaf(f_h, __uint_as_float(r[g & 1][j8 * 8 + j]), p_h));
+                                uint4 pk;
+                                pk.x = pack_half2(v[0], v[1]); pk.y = pack_half2(v[2], v[3]);
+                                pk.z = pack_half2(v[4], v[5]); pk.w = pack_half2(v[6], v[7]);
+                                const uint32_t pt8 = (uint32_t)(g * 2 + j8);             // which group of 8 points (0..15)
+                                *reinterpret_cast<uint4*>(rowp + (pt8 >> 3) * 1024u + (((pt8 & 7u) ^ sw) << 4)) = pk;
+                            }
+                        }
+                    }
+                } else {
+                    mbar_wait(my_acc, n_acc & 1);
+                    ++n_acc;
+                    tc_fence_after();
+                    tr.log('W', tl, s, 0);
+                    if (sop.epi == EPI_HEAD_TRUNK) {
+                        if (L.label_dim > 0) {
+                            uint32_t r[32];
+                            tc_ld32(t_lane, r);
+                            tc_wait_ld();
+                            if (valid) {
+                                const float inv_scale = __ldg(label_w + FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL);
+#pragma unroll
+                                for (int o = 0; o < 32; ++o) {
+                                    if (o < L.label_dim)
+                                        a.out[flat * C + o] = fmaf(__uint_as_float(r[o]), inv_scale, __ldg(label_w + FENERF_MAX_LABEL * FN_H + o));
+                                    else if (o == L.label_dim)
+                                        a.out[flat * C + (C - 1)] = __uint_as_float(r[o]) + __ldg(sigma_w + FN_H);
+                                }
+                            }
+                        } else {
+                            uint32_t r[8];
+                            tc_ld8(t_lane, r);
+                            tc_wait_ld();
+                            if (valid) a.out[flat * C + (C - 1)] = __uint_as_float(r[0]) + __ldg(sigma_w + FN_H);
+                        }
+                    } else {
+                        uint32_t r[8];
+                        tc_ld8(t_lane, r);
+                        tc_wait_ld();
+                        if (valid) {
+#pragma unroll
+                            for (int o = 0; o < 3; ++o) {
+                                const float x = __uint_as_float(r[o]) + __ldg(rgb_w + 3 * FN_H + o);
+                                a.out[flat * C + L.label_dim + o] = __fdividef(1.f, 1.f + __expf(-x));
+                            }
+                        }
+                    }
+                }
+                tr.log('D', tl, s, 0);
+                if (!last) {
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(my_aready);
+                }
+            }
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host: the per-tile stage / load program ------------------------------------------------------
+LoadOp* push(Fast3Args& A) { LoadOp* op = &A.loads[A.n_loads++]; memset(op, 0, sizeof(*op)); op->n_chunks = 1; op->w_is_a = 1; return op; }
+
+void push_film_pair(Fast3Args& A, size_t img_off, int half, int pair, bool first) {
+    LoadOp* op = push(A);
+    op->src = (uint32_t)(img_off + (size_t)half * 65536 + (size_t)pair * STAGE_BYTES);
+    op->bytes16 = STAGE_BYTES / 16; op->x_chunk = (uint8_t)(pair * 2); op->n_chunks = 2; op->k0 = 0; op->nk = 4; op->n8 = TILE / 8;
+    op->half = (uint8_t)half; op->first = first ? 1 : 0;
+}
+
+void push_x(Fast3Args& A, size_t img_off, uint8_t kind, int k0, int nk, bool first) {
+    LoadOp* op = push(A);       // the whole [256 features][64 slots] image, 32 KB: halves 16 KB apart
+    op->src = (uint32_t)img_off; op->bytes16 = 32768 / 16; op->k0 = (uint8_t)k0; op->nk = (uint8_t)nk; op->n8 = TILE / 8;
+    op->first = first ? 1 : 0; op->xkind = kind;
+}
+
+void push_head(Fast3Args& A, size_t img_off, int img_rows, int n) {
+    LoadOp* op = push(A);
+    op->src = (uint32_t)img_off;
+    op->bytes16 = (uint16_t)((4 * img_rows * FN_KCHUNK * 2) / 16); op->x_chunk = 0; op->n_chunks = 4; op->k0 = 0; op->nk = 4;
+    op->n8 = (uint8_t)(n / 8); op->half = 0; op->first = 1; op->w_is_a = 0;
+}
+
+bool build_program(const FnLayout& L, Fast3Args& A) {
+    A.n_loads = 0; A.n_stages = 0;
+    auto end_stage = [&](uint8_t epi, uint8_t film, int l0) -> StageOp& {
+        StageOp& st = A.stages[A.n_stages++];
+        memset(&st, 0, sizeof(st));
+        st.epi = epi; st.film = film; st.n_loads = (uint8_t)(A.n_loads - l0);
+        return st;
+    };
+    {
+        int l0 = A.n_loads;
+        push_x(A, L.first_img, X_POS, 0, 1, true);
+        end_stage(EPI_FILM, 0, l0);
+    }
+    for (int l = 0; l < L.n_hidden; ++l) {
+        if (l == L.trunk_hidden) {
+            int l0 = A.n_loads;
+            push_head(A, L.head_img, 32, L.label_dim > 0 ? 32 : 8);
+            end_stage(EPI_HEAD_TRUNK, 0, l0);
+        }
+        const bool c0 = (l == L.trunk_hidden);
+        int l0 = A.n_loads;
+        push_film_pair(A, L.hid_img[l], 0, 0, true);
+        push_film_pair(A, L.hid_img[l], 0, 1, false);
+        push_film_pair(A, L.hid_img[l], 1, 0, true);
+        push_film_pair(A, L.hid_img[l], 1, 1, false);
+        if (c0) push_x(A, L.color0_ximg, X_EXTRA, 1, L.grid_channels > 0 ? 3 : 1, false);
+        StageOp& st = end_stage(EPI_FILM, (uint8_t)(l + 1), l0);
+        st.uniform = c0 ? 0 : 1;
+        st.xsync = c0 ? 1 : 0;
+        if (A.n_loads > MAX_LOADS - 8 || A.n_stages > MAX_STAGES - 3) return false;
+    }
+    {
+        int l0 = A.n_loads;
+        push_head(A, L.rgb_img, 8, 8);
+        end_stage(EPI_HEAD_RGB, 0, l0);
+    }
+    return true;
+}
+
+}  // namespace
+
+int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
+                       const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
+                       long long* trace, cudaStream_t st) {
+    static_assert(sizeof(Fast3Args) <= 4000, "kernel parameter block too large");
+    static_assert(SMEM_TOTAL <= 232448, "one CTA per SM: 227 KB of shared memory");
+    FN_REQUIRE(L.trunk_hidden >= 1 && L.n_hidden - L.trunk_hidden >= 1, "field needs >= 2 trunk and >= 1 colour layers");
+    FN_REQUIRE(L.label_dim < 32, "the tcgen05 path packs labels and sigma into one 32-row head (label_dim <= 31)");
+    Fast3Args a;
+    memset(&a, 0, sizeof(a));
+    FN_REQUIRE(build_program(L, a), "field too deep for the stage program");
+    a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out;
+    a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
+    a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs; a.trace = trace;
+    if (a.n_tiles <= 0) return 0;
+    FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);
+    const long long n_pairs = (a.n_tiles + 1) / 2;
+    auto kernel = a.trace ? siren_fast3_kernel<true> : siren_fast3_kernel<false>;
+    FN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    int blocks = (int)(n_pairs < (long long)num_sms() ? n_pairs : (long long)num_sms());
+    kernel<<<blocks, NTHREADS, SMEM_TOTAL, st>>>(a);
+    FN_LAUNCH_OK("siren_fast3_kernel");
+    return 0;
+}
+
+}  // namespace fn
