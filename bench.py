@@ -317,6 +317,9 @@ def field_roofline(gen, args, latents, md, device):
         for it in range(4):
             pts, z, dirs, org = ops.ray_setup(rd, x_lin, y_lin, z_lin, c2w, torch.rand(B, N, S, 1, device=device))
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            # keep the GPU busy (~2 ms spin) while the host queues the launches below, so the events
+            # bracket kernel execution and not Python launch latency on an idle GPU
+            torch.cuda._sleep(4_000_000)
             e[0].record()
             raw_c = ops.siren_points(gen.siren, pts.reshape(B, N * S, 3), film, dirs, precision=rd.precision)
             e[1].record()

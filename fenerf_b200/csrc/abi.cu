@@ -55,8 +55,9 @@ int run_field(const FnLayout& L, const void* packed, const float* points, const 
     const unsigned char* pk = static_cast<const unsigned char*>(packed);
     if (precision == FENERF_PRECISION_EXACT)
         return siren_points_exact(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, nullptr, 0, out, st);
-    // two generations of the tcgen05 kernel; FENERF_B200_FAST_KERNEL=1 selects the paired-tile one
-    static const int which = [] { const char* e = getenv("FENERF_B200_FAST_KERNEL"); return e ? atoi(e) : 1; }();
+    // three generations of the tcgen05 kernel; the third is the default,
+    // FENERF_B200_FAST_KERNEL=1 / 2 select the earlier ones for comparison
+    static const int which = [] { const char* e = getenv("FENERF_B200_FAST_KERNEL"); return e ? atoi(e) : 3; }();
     if (which == 3)
         return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), st);
     if (which == 2)

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "siren_common.cuh"
 #include "tc5.cuh"
+#include <type_traits>
 
 namespace fn {
 
@@ -121,17 +122,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     const FnLayout& L = a.L;
 
     if (warp < RING) {
-        // ================= weight producers: load j of a (stage, tile) job -> slot j % RING = warp j % RING
+        // ================= weight producers: global load number `it` -> slot it % RING = producer warp it % RING.
+        // (Round-robin over ALL loads, not per stage: a slot is then always reused RING loads later, so the
+        // first load of a phase was requested two rounds before the previous phase ended.)
         if (lane == 0) {
-            uint32_t uses = 0;
+            uint32_t it = 0, uses = 0;
             for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x) {
                 const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
                 int li = 0;
                 for (int s = 0; s < a.n_stages; ++s) {
                     const int n = a.stages[s].n_loads;
                     for (int t = 0; t < nt; ++t)
-                        for (int j = warp; j < n; j += RING, ++uses) {
+                        for (int j = 0; j < n; ++j, ++it) {
+                            if ((int)(it % RING) != warp) continue;
                             mbar_wait(bar_empty + 8 * warp, (uses & 1) ^ 1);
+                            ++uses;
                             const uint32_t bytes = (uint32_t)a.loads[li + j].bytes16 * 16u;
                             mbar_arrive_expect_tx(bar_full + 8 * warp, bytes);
                             bulk_g2s(sbase + SMEM_RING + warp * STAGE_BYTES, a.packed + a.loads[li + j].src, bytes, bar_full + 8 * warp);
@@ -142,7 +147,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         }
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer (warp-converged; an elected lane issues) =================
-        uint32_t used[RING] = {0, 0, 0};
+        uint32_t used[RING] = {0, 0, 0};            // per-slot use counts (phase parity)
+        uint32_t it = 0;                            // global load number (slot = it % RING), as in the producers
         uint32_t n_ready[2] = {0, 0}, n_x[2] = {0, 0};
         Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, 1);
         const uint32_t ring_lo = (sbase + SMEM_RING) >> 4;
@@ -160,33 +166,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     const uint32_t x_lo0 = (sbase + t * TILE_SMEM) >> 4;      // activation chunk 0 of this tile
                     const uint32_t d0 = tmem_base + (uint32_t)t * 256u;
                     if (sop.uniform) {
-                        // straight-line: 4 rounds x 8 MMAs in ring slots 0,1,2,0: [h0 k01][h0 k23][h1 k01][h1 k23]
-                        constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);      // B (activations) MN-major
-                        constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
-                        mbar_wait(bar_full, used[0] & 1);
-                        tc_fence_after();
+                        // straight-line: 4 rounds x 8 MMAs, [h0 k01][h0 k23][h1 k01][h1 k23], in ring slots
+                        // s0, s0+1, s0+2, s0 (mod 3); one unrolled copy per starting slot so that every
+                        // descriptor word is a base plus an immediate
+                        auto issue = [&](auto s0_tag) {
+                            constexpr int S0 = decltype(s0_tag)::value;
+                            constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);      // B (activations) MN-major
+                            constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
+                            mbar_wait(bar_full + 8 * S0, used[S0] & 1);
+                            tc_fence_after();
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int slot = jj % RING;
-                            tr.log('F', tl, s, t * 64 + jj);
+                            for (int jj = 0; jj < 4; ++jj) {
+                                constexpr int dummy = 0; (void)dummy;
+                                const int slot = (S0 + jj) % RING;
+                                tr.log('F', tl, s, t * 64 + jj);
 #pragma unroll
-                            for (int c = 0; c < 2; ++c)
+                                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (c == 1 && k == 0 && jj < 3) {   // next slot's wait overlaps this slot's MMAs
-                                        const int ns = (jj + 1) % RING;
-                                        mbar_wait(bar_full + 8 * ns, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
-                                        tc_fence_after();
+                                    for (int k = 0; k < 4; ++k) {
+                                        if (c == 1 && k == 0 && jj < 3) {   // next slot's wait overlaps this slot's MMAs
+                                            const int ns = (S0 + jj + 1) % RING;
+                                            mbar_wait(bar_full + 8 * ns, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
+                                            tc_fence_after();
+                                        }
+                                        tc_mma_f16_elect(d0 + (jj >> 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kSlot16 + c * kChunk16 + 2 * k),
+                                                         kDescHiMN | (uint64_t)(x_lo0 + ((jj & 1) * 2 + c) * kChunk16 + 256 * k), idesc,
+                                                         ((jj & 1) == 0 && c == 0 && k == 0) ? 0u : 1u);
                                     }
-                                    tc_mma_f16_elect(d0 + (jj >> 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kSlot16 + c * kChunk16 + 2 * k),
-                                                     kDescHiMN | (uint64_t)(x_lo0 + ((jj & 1) * 2 + c) * kChunk16 + 256 * k), idesc,
-                                                     ((jj & 1) == 0 && c == 0 && k == 0) ? 0u : 1u);
-                                }
-                            tc_commit_elect(bar_empty + 8 * slot);
-                        }
-                        used[0] += 2; used[1] += 1; used[2] += 1;
+                                tc_commit_elect(bar_empty + 8 * slot);
+                            }
+                            used[S0] += 2; used[(S0 + 1) % RING] += 1; used[(S0 + 2) % RING] += 1;
+                        };
+                        const uint32_t s0 = it % RING;
+                        if (s0 == 0) issue(std::integral_constant<int, 0>{});
+                        else if (s0 == 1) issue(std::integral_constant<int, 1>{});
+                        else issue(std::integral_constant<int, 2>{});
+                        it += 4;
                     } else {
-                        for (int j = 0; j < sop.n_loads; ++j) {
+                        for (int j = 0; j < sop.n_loads; ++j, ++it) {
                             const LoadOp op = a.loads[li + j];
                             if (op.xkind == X_EXTRA) {
                                 // the main MMAs of this colour layer must retire before chunk 0 is overwritten with
@@ -197,7 +214,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                 tc_fence_after();
                                 tr.log('X', tl, s, t);
                             }
-                            const uint32_t slot = (uint32_t)j % RING;
+                            const uint32_t slot = it % RING;
                             const uint32_t cnt = slot == 0 ? used[0] : slot == 1 ? used[1] : used[2];
                             mbar_wait(bar_full + 8 * slot, cnt & 1);
                             tc_fence_after();
