@@ -16,6 +16,7 @@ namespace {
 
 constexpr int kMaxSamples = 128;   // 2 * 64
 constexpr int kRaysPerBlock = 8;   // one warp per ray
+constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ float softplus_torch(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
@@ -27,85 +28,145 @@ struct CompositeArgs {
     const float *raw_c, *z_c, *raw_f, *z_f, *noise;
     float *pixels, *depth, *wsum, *weights;
     int32_t* sort_idx;
+    int n_pad, warp_floats;        // shared-memory plan, see composite()
 };
 
+// Per-warp shared memory: z[n_pad] (unsorted depths, +inf padded), zs[n_pad] (sorted), w[n_pad],
+// ord[n_pad] (sorted position -> concatenated sample index), raw[n * C] (the ray's network outputs in
+// concatenation order [fine, coarse], staged with coalesced loads so the gathers below hit shared
+// memory instead of issuing one dependent global load per sample).
+//
+// Rounding: alpha / transmittance terms are the reference's op for op; the transmittance product,
+// the weight sum and the per-channel sums are warp-parallel (scan / tree) instead of torch's
+// left-to-right order, a difference of a few ulp per ray.
 __global__ void __launch_bounds__(kRaysPerBlock * 32) composite_kernel(CompositeArgs A) {
-    __shared__ float s_z[kRaysPerBlock][kMaxSamples];      // unsorted, then sorted depths
-    __shared__ float s_zs[kRaysPerBlock][kMaxSamples];
-    __shared__ int s_ord[kRaysPerBlock][kMaxSamples];      // sorted position -> original sample
-    __shared__ float s_a[kRaysPerBlock][kMaxSamples];
-    __shared__ float s_t[kRaysPerBlock][kMaxSamples];
-    __shared__ float s_w[kRaysPerBlock][kMaxSamples];
+    extern __shared__ __align__(16) float dyn[];
     __shared__ float s_out[FENERF_MAX_LABEL + 8][kRaysPerBlock + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = A.n_samples, S = A.S, C = A.C;
+    const int n = A.n_samples, S = A.S, C = A.C, np = A.n_pad;
     const bool hier = (n != S);
+    float* z = dyn + (size_t)warp * A.warp_floats;
+    float* zs = z + np;
+    float* w = zs + np;
+    int* ord = reinterpret_cast<int*>(w + np);
+    float* raw = w + 2 * np;
+    // lanes = (slice, channel) for the weighted sums: Cp = next power of two >= C
+    int Cp = 2;
+    while (Cp < C) Cp <<= 1;
+    const int ch = lane & (Cp - 1), slice = lane / Cp, n_slices = 32 / Cp;
     const long long n_groups = (A.n_rays + kRaysPerBlock - 1) / kRaysPerBlock;
 
     for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const long long ray = grp * kRaysPerBlock + warp;
         const bool valid = ray < A.n_rays;
         if (valid) {
-            float* z = s_z[warp];
-            float* zs = s_zs[warp];
-            int* ord = s_ord[warp];
-            float* a = s_a[warp];
-            float* t = s_t[warp];
-            float* w = s_w[warp];
             const long long base = ray * S;
-            // concatenation order of the reference: [fine, coarse]
-            for (int i = lane; i < n; i += 32) z[i] = hier ? (i < S ? A.z_f[base + i] : A.z_c[base + i - S]) : A.z_c[base + i];
-            __syncwarp();
-            // stable rank sort (ties keep concatenation order; torch.sort is unstable there, ties
-            // have measure zero)
-            for (int i = lane; i < n; i += 32) {
-                float zi = z[i];
-                int r = 0;
-                for (int j = 0; j < n; ++j) {
-                    float zj = z[j];
-                    r += (zj < zi) || (zj == zi && j < i);
+            // ---- stage depths and raw outputs; concatenation order of the reference: [fine, coarse]
+            for (int i = lane; i < np; i += 32)
+                z[i] = i < n ? (hier ? (i < S ? A.z_f[base + i] : A.z_c[base + i - S]) : A.z_c[base + i]) : INFINITY;
+            {
+                const int run = S * C;
+                const float* g0 = (hier ? A.raw_f : A.raw_c) + base * C;
+                const float* g1 = A.raw_c + base * C;
+                if ((run & 3) == 0 && ((reinterpret_cast<uintptr_t>(g0) | reinterpret_cast<uintptr_t>(g1)) & 15) == 0) {
+                    const float4* v0 = reinterpret_cast<const float4*>(g0);
+                    const float4* v1 = reinterpret_cast<const float4*>(g1);
+                    float4* d = reinterpret_cast<float4*>(raw);
+                    const int q = run >> 2;
+                    for (int i = lane; i < q; i += 32) d[i] = v0[i];
+                    if (hier) for (int i = lane; i < q; i += 32) d[q + i] = v1[i];
+                } else {
+                    for (int i = lane; i < run; i += 32) raw[i] = g0[i];
+                    if (hier) for (int i = lane; i < run; i += 32) raw[run + i] = g1[i];
                 }
-                zs[r] = zi;
-                ord[r] = i;
             }
             __syncwarp();
-            for (int j = lane; j < n; j += 32) {
-                int o = ord[j];
-                const float* src = hier ? (o < S ? A.raw_f + (base + o) * C : A.raw_c + (base + o - S) * C)
-                                        : A.raw_c + (base + o) * C;
-                float sig = src[C - 1];
-                if (A.noise) sig = __fadd_rn(sig, __fmul_rn(A.noise[ray * n + j], A.noise_std));
-                float delta = (j < n - 1) ? __fsub_rn(zs[j + 1], zs[j]) : 1e10f;
-                float act = A.clamp_mode == FENERF_CLAMP_RELU ? fmaxf(sig, 0.f) : softplus_torch(sig);
-                float alpha = __fsub_rn(1.f, expf(__fmul_rn(-delta, act)));
-                a[j] = alpha;
-                t[j] = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+            // ---- rank sort.  The fast pass counts strictly smaller depths; equal depths (measure
+            // zero) collide on one rank: the loser of the write sees it and the warp redoes the ranks
+            // with the stable tie rule (ties keep concatenation order).
+            int rank[kMaxSamples / 32];
+#pragma unroll
+            for (int k = 0; k < kMaxSamples / 32; ++k) {
+                const int i = lane + 32 * k;
+                if (i < n) {
+                    const float zi = z[i];
+                    const float4* z4 = reinterpret_cast<const float4*>(z);
+                    int r = 0;
+                    for (int j = 0; j < (np >> 2); ++j) {
+                        const float4 v = z4[j];
+                        r += (v.x < zi) + (v.y < zi) + (v.z < zi) + (v.w < zi);
+                    }
+                    rank[k] = r;
+                    zs[r] = zi;
+                    ord[r] = i;
+                }
             }
             __syncwarp();
-            for (int j = lane; j < n; j += 32) {
-                float T = 1.f;
-                for (int q = 0; q < j; ++q) T = __fmul_rn(T, t[q]);
-                w[j] = __fmul_rn(a[j], T);
+            bool clash = false;
+#pragma unroll
+            for (int k = 0; k < kMaxSamples / 32; ++k) {
+                const int i = lane + 32 * k;
+                if (i < n) clash |= (ord[rank[k]] != i);
             }
-            __syncwarp();
-            float wsum = 0.f;
-            for (int j = 0; j < n; ++j) wsum = __fadd_rn(wsum, w[j]);
-            if (A.last_back) {
+            if (__any_sync(kFull, clash)) {
                 __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    const float zi = z[i];
+                    int r = 0;
+                    for (int j = 0; j < n; ++j) {
+                        const float zj = z[j];
+                        r += (zj < zi) || (zj == zi && j < i);
+                    }
+                    zs[r] = zi;
+                    ord[r] = i;
+                }
+                __syncwarp();
+            }
+            // ---- alpha, transmittance (exclusive product scan over the sorted order), weights
+            float carry = 1.f, wpart = 0.f;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                float alpha = 0.f, t = 1.f;
+                if (j < n) {
+                    const int o = ord[j];
+                    float sig = raw[o * C + (C - 1)];
+                    if (A.noise) sig = __fadd_rn(sig, __fmul_rn(A.noise[ray * n + j], A.noise_std));
+                    const float delta = (j < n - 1) ? __fsub_rn(zs[j + 1], zs[j]) : 1e10f;
+                    const float act = A.clamp_mode == FENERF_CLAMP_RELU ? fmaxf(sig, 0.f) : softplus_torch(sig);
+                    alpha = __fsub_rn(1.f, expf(__fmul_rn(-delta, act)));
+                    t = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+                }
+                float p = t;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float q = __shfl_up_sync(kFull, p, off);
+                    if (lane >= off) p = __fmul_rn(p, q);
+                }
+                float excl = __shfl_up_sync(kFull, p, 1);
+                if (lane == 0) excl = 1.f;
+                const float wj = __fmul_rn(alpha, __fmul_rn(carry, excl));
+                if (j < n) { w[j] = wj; wpart = __fadd_rn(wpart, wj); }
+                carry = __fmul_rn(carry, __shfl_sync(kFull, p, 31));
+            }
+            float wsum = wpart;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) wsum = __fadd_rn(wsum, __shfl_xor_sync(kFull, wsum, off));
+            __syncwarp();
+            if (A.last_back) {
                 if (lane == 0) w[n - 1] = __fadd_rn(w[n - 1], __fsub_rn(1.f, wsum));
                 __syncwarp();
             }
-            // lanes = channels: c < C-1 colour/label channels, lane C-1 accumulates depth
+            // ---- weighted sums: channel c < C-1 colour / label, channel C-1 accumulates depth
             float acc = 0.f;
-            if (lane < C) {
-                for (int j = 0; j < n; ++j) {
-                    int o = ord[j];
-                    const float* src = hier ? (o < S ? A.raw_f + (base + o) * C : A.raw_c + (base + o - S) * C)
-                                            : A.raw_c + (base + o) * C;
-                    float v = lane < C - 1 ? src[lane] : zs[j];
-                    acc = __fadd_rn(acc, __fmul_rn(w[j], v));
+            if (ch < C) {
+                if (ch < C - 1) {
+                    for (int j = slice; j < n; j += n_slices) acc = fmaf(w[j], raw[ord[j] * C + ch], acc);
+                } else {
+                    for (int j = slice; j < n; j += n_slices) acc = fmaf(w[j], zs[j], acc);
                 }
             }
+            for (int off = Cp; off < 32; off <<= 1) acc = __fadd_rn(acc, __shfl_xor_sync(kFull, acc, off));
+            // lanes < Cp now hold the full sum of channel `lane`
             if (lane == C - 1 && A.depth) A.depth[ray] = acc;
             if (lane == 0 && A.wsum) A.wsum[ray] = wsum;
             if (A.weights) for (int j = lane; j < n; j += 32) A.weights[ray * n + j] = w[j];
@@ -136,10 +197,10 @@ __global__ void __launch_bounds__(kRaysPerBlock * 32) composite_kernel(Composite
                 const int n_seg = A.C_img - 3;
                 float x = lane < n_seg ? s_out[lane][warp] : -INFINITY;
                 float m = x;
-                for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, off));
                 float e = lane < n_seg ? expf(__fsub_rn(x, m)) : 0.f;
                 float sum = e;
-                for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(kFull, sum, off);
                 if (lane < n_seg) s_out[lane][warp] = __fdiv_rn(e, sum);
             }
         }
@@ -181,10 +242,20 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
     A.raw_c = raw_c; A.z_c = z_c; A.raw_f = raw_f; A.z_f = z_f; A.noise = noise;
     A.pixels = pixels; A.depth = depth; A.wsum = wsum; A.weights = weights; A.sort_idx = sort_idx;
     if (rd->hierarchical) FN_REQUIRE(raw_f && z_f, "hierarchical render needs raw_fine and z_fine");
+    A.n_pad = (A.n_samples + 3) & ~3;
+    A.warp_floats = (4 * A.n_pad + A.n_samples * C + 3) & ~3;
+    const size_t smem = (size_t)kRaysPerBlock * A.warp_floats * sizeof(float);
+    static size_t smem_allowed = 48 * 1024;
+    if (smem > smem_allowed) {
+        FN_CUDA_OK(cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_allowed = smem;
+    }
     long long groups = (A.n_rays + kRaysPerBlock - 1) / kRaysPerBlock;
-    int blocks = (int)(groups < (long long)num_sms() * 8 ? groups : (long long)num_sms() * 8);
+    int per_sm = (int)(200 * 1024 / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    int blocks = (int)(groups < (long long)num_sms() * per_sm ? groups : (long long)num_sms() * per_sm);
     if (blocks < 1) blocks = 1;
-    composite_kernel<<<blocks, kRaysPerBlock * 32, 0, st>>>(A);
+    composite_kernel<<<blocks, kRaysPerBlock * 32, smem, st>>>(A);
     FN_LAUNCH_OK("composite_kernel");
     return 0;
 }

@@ -70,10 +70,13 @@ resample_kernel(long long n_rays, long long rays_per_batch, int S, int C, int cl
         __syncwarp();
         float total = 0.f;
         for (int j = 0; j < S - 2; ++j) total = __fadd_rn(total, w[j]);   // every lane, same order
+        __syncwarp();
+        for (int j = lane; j < S - 2; j += 32) w[j] = __fdiv_rn(w[j], total);   // pdf, one division per bin
+        __syncwarp();
         // cdf[0] = 0, cdf[j+1] = cdf[j] + pdf[j]   (S-1 entries)
         for (int i = lane; i < S - 1; i += 32) {
             float c = 0.f;
-            for (int j = 0; j < i; ++j) c = __fadd_rn(c, __fdiv_rn(w[j], total));
+            for (int j = 0; j < i; ++j) c = __fadd_rn(c, w[j]);
             cdf[i] = c;
         }
         __syncwarp();
