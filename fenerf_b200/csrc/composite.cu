@@ -31,6 +31,36 @@ struct CompositeArgs {
     int n_pad, warp_floats;        // shared-memory plan, see composite()
 };
 
+// One sweep over the (padded) depths ranks the NK samples a lane owns: rank = number of strictly
+// smaller depths.  Shared-memory reads are 16-byte broadcasts shared by the NK counters.
+template <int NK>
+__device__ __forceinline__ void rank_pass(const float* z, float* zs, int* ord, int n, int np, int lane,
+                                          int (&rank)[kMaxSamples / 32]) {
+    float zi[NK];
+    int r[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int i = lane + 32 * k;
+        zi[k] = i < n ? z[i] : INFINITY;
+        r[k] = 0;
+    }
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    for (int j = 0; j < (np >> 2); ++j) {
+        const float4 v = z4[j];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) r[k] += (v.x < zi[k]) + (v.y < zi[k]) + (v.z < zi[k]) + (v.w < zi[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int i = lane + 32 * k;
+        rank[k] = r[k];
+        if (i < n) {
+            zs[r[k]] = zi[k];
+            ord[r[k]] = i;
+        }
+    }
+}
+
 // Per-warp shared memory: z[n_pad] (unsorted depths, +inf padded), zs[n_pad] (sorted), w[n_pad],
 // ord[n_pad] (sorted position -> concatenated sample index), raw[n * C] (the ray's network outputs in
 // concatenation order [fine, coarse], staged with coalesced loads so the gathers below hit shared
@@ -85,21 +115,11 @@ __global__ void __launch_bounds__(kRaysPerBlock * 32) composite_kernel(Composite
             // zero) collide on one rank: the loser of the write sees it and the warp redoes the ranks
             // with the stable tie rule (ties keep concatenation order).
             int rank[kMaxSamples / 32];
-#pragma unroll
-            for (int k = 0; k < kMaxSamples / 32; ++k) {
-                const int i = lane + 32 * k;
-                if (i < n) {
-                    const float zi = z[i];
-                    const float4* z4 = reinterpret_cast<const float4*>(z);
-                    int r = 0;
-                    for (int j = 0; j < (np >> 2); ++j) {
-                        const float4 v = z4[j];
-                        r += (v.x < zi) + (v.y < zi) + (v.z < zi) + (v.w < zi);
-                    }
-                    rank[k] = r;
-                    zs[r] = zi;
-                    ord[r] = i;
-                }
+            switch ((n + 31) >> 5) {
+                case 1: rank_pass<1>(z, zs, ord, n, np, lane, rank); break;
+                case 2: rank_pass<2>(z, zs, ord, n, np, lane, rank); break;
+                case 3: rank_pass<3>(z, zs, ord, n, np, lane, rank); break;
+                default: rank_pass<4>(z, zs, ord, n, np, lane, rank); break;
             }
             __syncwarp();
             bool clash = false;
@@ -204,17 +224,15 @@ __global__ void __launch_bounds__(kRaysPerBlock * 32) composite_kernel(Composite
                 if (lane < n_seg) s_out[lane][warp] = __fdiv_rn(e, sum);
             }
         }
-        __syncthreads();
-        // coalesced NCHW store: 8 consecutive rays per channel row, *2-1
-        for (int i = threadIdx.x; i < A.C_img * kRaysPerBlock; i += blockDim.x) {
-            int c = i / kRaysPerBlock, r = i % kRaysPerBlock;
-            long long rr = grp * kRaysPerBlock + r;
-            if (rr < A.n_rays) {
-                long long b = rr / A.rays_per_batch, p = rr % A.rays_per_batch;
-                A.pixels[(b * A.C_img + c) * A.rays_per_batch + p] = __fsub_rn(__fmul_rn(s_out[c][r], 2.f), 1.f);
-            }
+        if (valid) {
+            // NCHW store, *2-1: one 4-byte store per channel; the 8 warps of a block own 8 consecutive
+            // pixels of each channel row, so a row's stores merge in L2
+            __syncwarp();
+            const long long b = ray / A.rays_per_batch, p = ray % A.rays_per_batch;
+            for (int c = lane; c < A.C_img; c += 32)
+                A.pixels[(b * A.C_img + c) * A.rays_per_batch + p] = __fsub_rn(__fmul_rn(s_out[c][warp], 2.f), 1.f);
+            __syncwarp();
         }
-        __syncthreads();
     }
 }
 

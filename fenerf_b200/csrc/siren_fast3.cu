@@ -40,7 +40,8 @@ constexpr uint32_t STAGE_BYTES = 32768;
 constexpr uint32_t TILE_SMEM = 4 * CHUNK_BYTES;      // four activation chunks per tile
 constexpr uint32_t SMEM_RING = 2 * TILE_SMEM;
 constexpr uint32_t SMEM_BAR = SMEM_RING + RING * STAGE_BYTES;   // 229376
-constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
+constexpr uint32_t SMEM_TAB = SMEM_BAR + 256;                     // per-tile program: loads, then stages
+constexpr uint32_t SMEM_TOTAL = SMEM_TAB + 96 * 16 + 16 * 8;     // 231296
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_LOADS = 96;
 constexpr int MAX_STAGES = 16;
@@ -67,9 +68,11 @@ struct StageOp {
     uint8_t epi;           // EPI_*
     uint8_t film;          // FiLM layer index
     uint8_t n_loads;
-    uint8_t uniform;       // 1: plain 256x256 FiLM layer = 4 loads (h0 k01, h0 k23, h1 k01, h1 k23)
-    uint8_t xsync;         // index of the X_EXTRA load: before it the issuer commits `xmain` and waits `xready`
-    uint8_t pad[3];
+    uint8_t uniform;       // 1: 256x256 FiLM layer = 4 loads (h0 k01, h1 k01, h0 k23, h1 k23) [+ one X_EXTRA load]
+    uint8_t xsync;         // 1: a fifth, X_EXTRA load follows: before it the issuer commits `xmain` and waits `xready`
+    uint8_t l0;            // index of the stage's first load in Fast3Args::loads
+    uint8_t fuse_next;     // 1: the issuer runs the next stage of the SAME tile before turning to the other tile
+    uint8_t pad;
 };
 
 struct Fast3Args {
@@ -84,6 +87,7 @@ struct Fast3Args {
     float* out;
     long long ppb, tiles_per_batch, n_tiles;
     int dir_group, lock_dirs;
+    int debug_short_loads;
     long long* trace;
 };
 
@@ -100,6 +104,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     const uint32_t bar_xready = bar_xmain + 16;             // [2] colour layer 0: extra input slots written into chunk 0
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * RING + 8));
 
+    // The program tables are read once per load / stage by single threads on latency-critical paths
+    // (producer turnaround, issuer phase changes): keep them in shared memory, not in the constant bank.
+    LoadOp* s_loads = reinterpret_cast<LoadOp*>(smem + SMEM_TAB);
+    StageOp* s_stages = reinterpret_cast<StageOp*>(smem + SMEM_TAB + MAX_LOADS * sizeof(LoadOp));
+    for (int i = threadIdx.x; i < a.n_loads; i += NTHREADS) s_loads[i] = a.loads[i];
+    for (int i = threadIdx.x; i < a.n_stages; i += NTHREADS) s_stages[i] = a.stages[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         for (int t = 0; t < 2; ++t) {
@@ -129,19 +139,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
             uint32_t it = 0, uses = 0;
             for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x) {
                 const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
-                int li = 0;
-                for (int s = 0; s < a.n_stages; ++s) {
-                    const int n = a.stages[s].n_loads;
+                for (int s = 0; s < a.n_stages;) {
+                    int s_end = s + 1;
+                    while (s_stages[s_end - 1].fuse_next) ++s_end;
                     for (int t = 0; t < nt; ++t)
-                        for (int j = 0; j < n; ++j, ++it) {
-                            if ((int)(it % RING) != warp) continue;
-                            mbar_wait(bar_empty + 8 * warp, (uses & 1) ^ 1);
-                            ++uses;
-                            const uint32_t bytes = (uint32_t)a.loads[li + j].bytes16 * 16u;
-                            mbar_arrive_expect_tx(bar_full + 8 * warp, bytes);
-                            bulk_g2s(sbase + SMEM_RING + warp * STAGE_BYTES, a.packed + a.loads[li + j].src, bytes, bar_full + 8 * warp);
+                        for (int ss = s; ss < s_end; ++ss) {
+                            const int n = s_stages[ss].n_loads, li = s_stages[ss].l0;
+                            for (int j = 0; j < n; ++j, ++it) {
+                                if ((int)(it % RING) != warp) continue;
+                                const LoadOp op = s_loads[li + j];          // before the wait: off the turnaround path
+                                uint32_t bytes = (uint32_t)op.bytes16 * 16u;
+                                if (a.debug_short_loads) bytes = 1024u;     // timing experiment only: wrong results
+                                const unsigned char* src = a.packed + op.src;
+                                mbar_wait(bar_empty + 8 * warp, (uses & 1) ^ 1);
+                                ++uses;
+                                mbar_arrive_expect_tx(bar_full + 8 * warp, bytes);
+                                bulk_g2s(sbase + SMEM_RING + warp * STAGE_BYTES, src, bytes, bar_full + 8 * warp);
+                            }
                         }
-                    li += n;
+                    s = s_end;
                 }
             }
         }
@@ -152,113 +168,138 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         uint32_t n_ready[2] = {0, 0}, n_x[2] = {0, 0};
         Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, 1);
         const uint32_t ring_lo = (sbase + SMEM_RING) >> 4;
+        constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
+        // one ring slot's "full" wait for a single-load step (slot number is a runtime value here)
+        auto wait_full = [&](uint32_t slot) {
+            const uint32_t cnt = slot == 0 ? used[0] : slot == 1 ? used[1] : used[2];
+            mbar_wait(bar_full + 8 * slot, cnt & 1);
+            tc_fence_after();
+            if (slot == 0) ++used[0]; else if (slot == 1) ++used[1]; else ++used[2];
+        };
+        // stage flags as register bit masks: a phase change costs no memory access
+        uint32_t m_uniform = 0, m_xsync = 0, m_fuse = 0;
+        for (int i = 0; i < a.n_stages; ++i) {
+            m_uniform |= (uint32_t)(s_stages[i].uniform != 0) << i;
+            m_xsync |= (uint32_t)(s_stages[i].xsync != 0) << i;
+            m_fuse |= (uint32_t)(s_stages[i].fuse_next != 0) << i;
+        }
         int tl = 0;
         for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x, ++tl) {
             const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
-            int li = 0;
-            for (int s = 0; s < a.n_stages; ++s) {
-                const StageOp sop = a.stages[s];
+            for (int s = 0; s < a.n_stages;) {
+                int s_end = s + 1;
+                while ((m_fuse >> (s_end - 1)) & 1u) ++s_end;
                 for (int t = 0; t < nt; ++t) {
-                    mbar_wait(bar_aready + 8 * t, n_ready[t] & 1);
-                    ++n_ready[t];
-                    tc_fence_after();
-                    tr.log('A', tl, s, t);
-                    const uint32_t x_lo0 = (sbase + t * TILE_SMEM) >> 4;      // activation chunk 0 of this tile
-                    const uint32_t d0 = tmem_base + (uint32_t)t * 256u;
-                    if (sop.uniform) {
-                        // straight-line: 4 rounds x 8 MMAs, [h0 k01][h0 k23][h1 k01][h1 k23], in ring slots
-                        // s0, s0+1, s0+2, s0 (mod 3); one unrolled copy per starting slot so that every
-                        // descriptor word is a base plus an immediate
-                        auto issue = [&](auto s0_tag) {
-                            constexpr int S0 = decltype(s0_tag)::value;
-                            constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);      // B (activations) MN-major
-                            constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
-                            mbar_wait(bar_full + 8 * S0, used[S0] & 1);
-                            tc_fence_after();
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                constexpr int dummy = 0; (void)dummy;
-                                const int slot = (S0 + jj) % RING;
-                                tr.log('F', tl, s, t * 64 + jj);
-#pragma unroll
-                                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        if (c == 1 && k == 0 && jj < 3) {   // next slot's wait overlaps this slot's MMAs
-                                            const int ns = (S0 + jj + 1) % RING;
-                                            mbar_wait(bar_full + 8 * ns, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
-                                            tc_fence_after();
-                                        }
-                                        tc_mma_f16_elect(d0 + (jj >> 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kSlot16 + c * kChunk16 + 2 * k),
-                                                         kDescHiMN | (uint64_t)(x_lo0 + ((jj & 1) * 2 + c) * kChunk16 + 256 * k), idesc,
-                                                         ((jj & 1) == 0 && c == 0 && k == 0) ? 0u : 1u);
-                                    }
-                                tc_commit_elect(bar_empty + 8 * slot);
-                            }
-                            used[S0] += 2; used[(S0 + 1) % RING] += 1; used[(S0 + 2) % RING] += 1;
-                        };
-                        const uint32_t s0 = it % RING;
-                        if (s0 == 0) issue(std::integral_constant<int, 0>{});
-                        else if (s0 == 1) issue(std::integral_constant<int, 1>{});
-                        else issue(std::integral_constant<int, 2>{});
-                        it += 4;
-                    } else {
-                        for (int j = 0; j < sop.n_loads; ++j, ++it) {
-                            const LoadOp op = a.loads[li + j];
-                            if (op.xkind == X_EXTRA) {
-                                // the main MMAs of this colour layer must retire before chunk 0 is overwritten with
-                                // the extra input slots; then wait until the epilogue has written them
-                                tc_commit_elect(bar_xmain + 8 * t);
-                                mbar_wait(bar_xready + 8 * t, n_x[t] & 1);
-                                ++n_x[t];
-                                tc_fence_after();
-                                tr.log('X', tl, s, t);
-                            }
+                    for (int ss = s; ss < s_end; ++ss) {
+                        const bool st_uniform = (m_uniform >> ss) & 1u, st_xsync = (m_xsync >> ss) & 1u;
+                        tr.log('B', tl, ss, t);
+                        tr.log('b', tl, ss, t);       // calibration: back-to-back with 'B'
+                        mbar_wait(bar_aready + 8 * t, (t == 0 ? n_ready[0] : n_ready[1]) & 1);
+                        tr.log('a', tl, ss, t);
+                        if (t == 0) ++n_ready[0]; else ++n_ready[1];
+                        tc_fence_after();
+                        tr.log('A', tl, ss, t);
+                        const uint32_t x_lo0 = (sbase + t * TILE_SMEM) >> 4;      // activation chunk 0 of this tile
+                        const uint32_t d0 = tmem_base + (uint32_t)t * 256u;
+                        // K-major input slots (positions in chunk 3 / direction + grid features in chunk 0) against
+                        // the [256 features][64 slots] weight image: one MMA group per feature half
+                        auto x_load = [&](const LoadOp op) {
                             const uint32_t slot = it % RING;
-                            const uint32_t cnt = slot == 0 ? used[0] : slot == 1 ? used[1] : used[2];
-                            mbar_wait(bar_full + 8 * slot, cnt & 1);
-                            tc_fence_after();
-                            if (slot == 0) ++used[0]; else if (slot == 1) ++used[1]; else ++used[2];
-                            tr.log('F', tl, s, t * 64 + j);
-                            const uint32_t w_stride = ((uint32_t)op.bytes16 * 16u) / op.n_chunks;
-                            if (op.xkind != X_NONE) {
-                                // K-major input slots in chunk 3 (positions) or chunk 0 (direction / grid features);
-                                // the 32 KB slot holds the [256 features][64 slots] image: one MMA group per half
-                                const uint32_t x_lo = x_lo0 + (op.xkind == X_POS ? 3u : 0u) * (CHUNK_BYTES >> 4);
-                                const uint32_t idesc = umma_idesc_f16(TILE, 0, 0);
-#pragma unroll 1
-                                for (int h = 0; h < 2; ++h) {
-                                    const uint32_t w_lo = ring_lo + slot * (STAGE_BYTES >> 4) + (uint32_t)h * (16384u >> 4);
-#pragma unroll 1
-                                    for (int k = 0; k < op.nk; ++k) {
+                            wait_full(slot);
+                            tr.log('F', tl, ss, t * 64 + 4);
+                            const uint32_t x_lo = x_lo0 + (op.xkind == X_POS ? 3u : 0u) * kChunk16;
+                            constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 0);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t w_lo = ring_lo + slot * kSlot16 + (uint32_t)h * (16384u >> 4);
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                    if (k < op.nk) {
                                         const uint32_t ko = (uint32_t)(op.k0 + k) * 2u;
                                         tc_mma_f16_elect(d0 + h * 128, kDescHi | (uint64_t)(w_lo + ko), kDescHi | (uint64_t)(x_lo + ko),
                                                          idesc, (op.first && k == 0) ? 0u : 1u);
                                     }
-                                }
-                            } else {
-                                const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u, op.w_is_a ? 0u : 1u, op.w_is_a ? 1u : 0u);
-                                const uint32_t d_col = d0 + (uint32_t)op.half * 128u;
-#pragma unroll 1
-                                for (int c = 0; c < op.n_chunks; ++c) {
-                                    const uint32_t x_lo = x_lo0 + (uint32_t)(op.x_chunk + c) * (CHUNK_BYTES >> 4);
-                                    const uint32_t w_lo = ring_lo + slot * (STAGE_BYTES >> 4) + ((c * w_stride) >> 4);
-#pragma unroll 4
-                                    for (int k = 0; k < op.nk; ++k) {
-                                        const uint64_t xd = kDescHiMN | (uint64_t)(x_lo + (uint32_t)(op.k0 + k) * 256u);
-                                        const uint64_t wd = kDescHi | (uint64_t)(w_lo + (uint32_t)(op.k0 + k) * 2u);
-                                        tc_mma_f16_elect(d_col, op.w_is_a ? wd : xd, op.w_is_a ? xd : wd, idesc,
-                                                         (op.first && c == 0 && k == 0) ? 0u : 1u);
-                                    }
-                                }
                             }
                             tc_commit_elect(bar_empty + 8 * slot);
+                            ++it;
+                        };
+                        if (st_uniform) {
+                            // straight-line: 4 rounds x 8 MMAs, [h0 k01][h1 k01][h0 k23][h1 k23], in ring slots
+                            // s0, s0+1, s0+2, s0 (mod 3); one unrolled copy per starting slot so that every
+                            // descriptor word is a base plus an immediate
+                            auto issue = [&](auto s0_tag) {
+                                constexpr int S0 = decltype(s0_tag)::value;
+                                constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);      // B (activations) MN-major
+                                tr.log('f', tl, ss, t);
+                                mbar_wait(bar_full + 8 * S0, used[S0] & 1);
+                                tr.log('g', tl, ss, t);
+                                tc_fence_after();
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const int slot = (S0 + jj) % RING;
+                                    tr.log('F', tl, ss, t * 64 + jj);
+#pragma unroll
+                                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            if (c == 1 && k == 0 && jj < 3) {   // next slot's wait overlaps this slot's MMAs
+                                                const int ns = (S0 + jj + 1) % RING;
+                                                mbar_wait(bar_full + 8 * ns, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
+                                                tc_fence_after();
+                                            }
+                                            tc_mma_f16_elect(d0 + (jj & 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kSlot16 + c * kChunk16 + 2 * k),
+                                                             kDescHiMN | (uint64_t)(x_lo0 + ((jj >> 1) * 2 + c) * kChunk16 + 256 * k), idesc,
+                                                             ((jj >> 1) == 0 && c == 0 && k == 0) ? 0u : 1u);
+                                            if (jj == 0 && c == 0 && k == 0) tr.log('m', tl, ss, t);
+                                            if (jj == 3 && c == 1 && k == 3) tr.log('n', tl, ss, t);
+                                        }
+                                    tc_commit_elect(bar_empty + 8 * slot);
+                                    // first colour layer: chunks 0/1 have been read for the last time once [h0 k01] and
+                                    // [h1 k01] retire; the epilogue overwrites chunk 0 with the extra input slots while
+                                    // the k23 rounds run
+                                    if (jj == 1 && st_xsync) tc_commit_elect(bar_xmain + 8 * t);
+                                }
+                                used[S0] += 2; used[(S0 + 1) % RING] += 1; used[(S0 + 2) % RING] += 1;
+                            };
+                            const uint32_t s0 = it % RING;
+                            if (s0 == 0) issue(std::integral_constant<int, 0>{});
+                            else if (s0 == 1) issue(std::integral_constant<int, 1>{});
+                            else issue(std::integral_constant<int, 2>{});
+                            it += 4;
+                            if (st_xsync) {
+                                // wait until the epilogue has written the extra input slots into chunk 0
+                                mbar_wait(bar_xready + 8 * t, (t == 0 ? n_x[0] : n_x[1]) & 1);
+                                if (t == 0) ++n_x[0]; else ++n_x[1];
+                                tc_fence_after();
+                                tr.log('X', tl, ss, t);
+                                x_load(s_loads[s_stages[ss].l0 + 4]);
+                            }
+                        } else if (s_loads[s_stages[ss].l0].xkind != X_NONE) {
+                            x_load(s_loads[s_stages[ss].l0]);
+                        } else {
+                            // head: activations are the A operand (M = 128 points, MN-major), the [n rows][256] head
+                            // image the B operand; 4 k-chunks x 4 K-steps, fully unrolled
+                            const LoadOp op = s_loads[s_stages[ss].l0];
+                            const uint32_t slot = it % RING;
+                            wait_full(slot);
+                            tr.log('F', tl, ss, t * 64);
+                            const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u, 1u, 0u);
+                            const uint32_t w_stride16 = ((uint32_t)op.bytes16) >> 2;      // bytes / 4 chunks / 16
+                            const uint32_t w_lo = ring_lo + slot * kSlot16;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma_f16_elect(d0, kDescHiMN | (uint64_t)(x_lo0 + c * kChunk16 + 256 * k),
+                                                     kDescHi | (uint64_t)(w_lo + c * w_stride16 + 2 * k), idesc, (c | k) ? 1u : 0u);
+                            tc_commit_elect(bar_empty + 8 * slot);
+                            ++it;
                         }
+                        tc_commit_elect(bar_acc + 8 * t);
+                        tr.log('C', tl, ss, t);
                     }
-                    tc_commit_elect(bar_acc + 8 * t);
-                    tr.log('C', tl, s, t);
                 }
-                li += sop.n_loads;
+                s = s_end;
             }
         }
     } else {
@@ -277,7 +318,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         const float* rgb_w = reinterpret_cast<const float*>(a.packed + L.rgb_w);
         const float* label_w = reinterpret_cast<const float*>(a.packed + L.label_w);
         uint32_t n_acc = 0, n_x = 0;
-        Tracer<kTrace> tr((warp == EPI_WARP0 || warp == EPI_WARP0 + 4) && lane == 0 ? a.trace : nullptr, 2 + t);
+        // traced: quadrant-0 warp of each tile (roles 2, 3) and the quadrant-3 warp of tile X (role 0; it shares
+        // its scheduler with the MMA issuer)
+        Tracer<kTrace> tr((q == 0 || (q == 3 && t == 0)) && lane == 0 ? a.trace : nullptr, q == 0 ? 2 + t : 0);
         int tl = 0;
         for (long long pair = blockIdx.x; pair * 2 + t < a.n_tiles; pair += gridDim.x, ++tl) {
             const long long tile = pair * 2 + t;
@@ -332,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
             if (lane == 0) mbar_arrive(my_aready);
 
             for (int s = 0; s < a.n_stages; ++s) {
-                const StageOp sop = a.stages[s];
+                const StageOp sop = s_stages[s];
                 const bool last = (s + 1 == a.n_stages);
                 if (sop.epi == EPI_FILM) {
                     const int fl = row;
@@ -475,7 +518,7 @@ bool build_program(const FnLayout& L, Fast3Args& A) {
     auto end_stage = [&](uint8_t epi, uint8_t film, int l0) -> StageOp& {
         StageOp& st = A.stages[A.n_stages++];
         memset(&st, 0, sizeof(st));
-        st.epi = epi; st.film = film; st.n_loads = (uint8_t)(A.n_loads - l0);
+        st.epi = epi; st.film = film; st.n_loads = (uint8_t)(A.n_loads - l0); st.l0 = (uint8_t)l0;
         return st;
     };
     {
@@ -487,17 +530,19 @@ bool build_program(const FnLayout& L, Fast3Args& A) {
         if (l == L.trunk_hidden) {
             int l0 = A.n_loads;
             push_head(A, L.head_img, 32, L.label_dim > 0 ? 32 : 8);
-            end_stage(EPI_HEAD_TRUNK, 0, l0);
+            // the head and the first colour layer of a tile are issued back to back: the other tile is in
+            // its long epilogue meanwhile, and would otherwise hold the in-order issuer at its own head
+            end_stage(EPI_HEAD_TRUNK, 0, l0).fuse_next = 1;
         }
         const bool c0 = (l == L.trunk_hidden);
         int l0 = A.n_loads;
         push_film_pair(A, L.hid_img[l], 0, 0, true);
-        push_film_pair(A, L.hid_img[l], 0, 1, false);
         push_film_pair(A, L.hid_img[l], 1, 0, true);
+        push_film_pair(A, L.hid_img[l], 0, 1, false);
         push_film_pair(A, L.hid_img[l], 1, 1, false);
         if (c0) push_x(A, L.color0_ximg, X_EXTRA, 1, L.grid_channels > 0 ? 3 : 1, false);
         StageOp& st = end_stage(EPI_FILM, (uint8_t)(l + 1), l0);
-        st.uniform = c0 ? 0 : 1;
+        st.uniform = 1;
         st.xsync = c0 ? 1 : 0;
         if (A.n_loads > MAX_LOADS - 8 || A.n_stages > MAX_STAGES - 3) return false;
     }
@@ -524,6 +569,10 @@ int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const flo
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out;
     a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
     a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs; a.trace = trace;
+    {
+        const char* e = getenv("FENERF_B200_DEBUG_SHORT_LOADS");   // profiling aid, see tools/diag_fast.py
+        a.debug_short_loads = (e && atoi(e)) ? 1 : 0;
+    }
     if (a.n_tiles <= 0) return 0;
     FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);
     const long long n_pairs = (a.n_tiles + 1) / 2;

@@ -19,15 +19,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
                  : "memory");
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+// try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware until the phase flips
+// instead of spinning through issue slots the epilogue warps on the same scheduler need; the clock
+// watchdog only runs on the (rare) path where a suspended wait timed out.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+    return done;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = 0;
-    for (uint32_t spin = 0;; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-        if (spin == 64) t0 = clock64();
-        if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
