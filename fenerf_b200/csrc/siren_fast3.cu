@@ -98,11 +98,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = sbase + SMEM_BAR;             // [RING]
     const uint32_t bar_empty = bar_full + 8 * RING;         // [RING]
-    const uint32_t bar_acc = bar_empty + 8 * RING;          // [2] accumulator of tile t complete (issuer -> epilogue t)
-    const uint32_t bar_aready = bar_acc + 16;               // [2] operand written + accumulator drained (epilogue t -> issuer)
-    const uint32_t bar_xmain = bar_aready + 16;             // [2] colour layer 0: main MMAs retired, chunk 0 reusable
+    // Accumulator / operand hand-offs are per tile AND per feature half h (index t * 2 + h): half h of the
+    // accumulator feeds activation chunks 2h, 2h+1 of the next layer, so the next layer's [h0 k01] MMAs can
+    // start while the epilogue is still working on half 1, and the epilogue of half 0 starts while the
+    // [h1 k23] MMAs are still running.
+    const uint32_t bar_acc = bar_empty + 8 * RING;          // [2][2] accumulator half complete (issuer -> epilogue t)
+    const uint32_t bar_aready = bar_acc + 32;               // [2][2] chunks 2h,2h+1 written + half h drained (epilogue t -> issuer)
+    const uint32_t bar_xmain = bar_aready + 32;             // [2] colour layer 0: k01 MMAs retired, chunk 0 reusable
     const uint32_t bar_xready = bar_xmain + 16;             // [2] colour layer 0: extra input slots written into chunk 0
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * RING + 8));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * RING + 12));
 
     // The program tables are read once per load / stage by single threads on latency-critical paths
     // (producer turnaround, issuer phase changes): keep them in shared memory, not in the constant bank.
@@ -113,8 +117,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         for (int t = 0; t < 2; ++t) {
-            mbar_init(bar_acc + 8 * t, 1);
-            mbar_init(bar_aready + 8 * t, 4);
+            for (int h = 0; h < 2; ++h) {
+                mbar_init(bar_acc + 8 * (t * 2 + h), 1);
+                mbar_init(bar_aready + 8 * (t * 2 + h), 4);
+            }
             mbar_init(bar_xmain + 8 * t, 1);
             mbar_init(bar_xready + 8 * t, 4);
         }
@@ -193,10 +199,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     for (int ss = s; ss < s_end; ++ss) {
                         const bool st_uniform = (m_uniform >> ss) & 1u, st_xsync = (m_xsync >> ss) & 1u;
                         tr.log('B', tl, ss, t);
-                        tr.log('b', tl, ss, t);       // calibration: back-to-back with 'B'
-                        mbar_wait(bar_aready + 8 * t, (t == 0 ? n_ready[0] : n_ready[1]) & 1);
-                        tr.log('a', tl, ss, t);
+                        const uint32_t rdy_par = (t == 0 ? n_ready[0] : n_ready[1]) & 1;
                         if (t == 0) ++n_ready[0]; else ++n_ready[1];
+                        mbar_wait(bar_aready + 8 * (t * 2), rdy_par);
+                        // a plain FiLM layer observes half 1 only before its [h1 k01] round (inside `issue`)
+                        if (!st_uniform) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
                         tc_fence_after();
                         tr.log('A', tl, ss, t);
                         const uint32_t x_lo0 = (sbase + t * TILE_SMEM) >> 4;      // activation chunk 0 of this tile
@@ -230,9 +237,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             auto issue = [&](auto s0_tag) {
                                 constexpr int S0 = decltype(s0_tag)::value;
                                 constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);      // B (activations) MN-major
-                                tr.log('f', tl, ss, t);
                                 mbar_wait(bar_full + 8 * S0, used[S0] & 1);
-                                tr.log('g', tl, ss, t);
                                 tc_fence_after();
 #pragma unroll
                                 for (int jj = 0; jj < 4; ++jj) {
@@ -245,19 +250,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                             if (c == 1 && k == 0 && jj < 3) {   // next slot's wait overlaps this slot's MMAs
                                                 const int ns = (S0 + jj + 1) % RING;
                                                 mbar_wait(bar_full + 8 * ns, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
+                                                // the [h1 k01] round needs accumulator half 1 drained (and, later, chunks 2,3)
+                                                if (jj == 0) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
                                                 tc_fence_after();
                                             }
                                             tc_mma_f16_elect(d0 + (jj & 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kSlot16 + c * kChunk16 + 2 * k),
                                                              kDescHiMN | (uint64_t)(x_lo0 + ((jj >> 1) * 2 + c) * kChunk16 + 256 * k), idesc,
                                                              ((jj >> 1) == 0 && c == 0 && k == 0) ? 0u : 1u);
-                                            if (jj == 0 && c == 0 && k == 0) tr.log('m', tl, ss, t);
-                                            if (jj == 3 && c == 1 && k == 3) tr.log('n', tl, ss, t);
                                         }
                                     tc_commit_elect(bar_empty + 8 * slot);
                                     // first colour layer: chunks 0/1 have been read for the last time once [h0 k01] and
                                     // [h1 k01] retire; the epilogue overwrites chunk 0 with the extra input slots while
                                     // the k23 rounds run
                                     if (jj == 1 && st_xsync) tc_commit_elect(bar_xmain + 8 * t);
+                                    // half 0 is complete after [h0 k23] (and chunks 0,1 were last read by [h1 k01])
+                                    if (jj == 2 && !st_xsync) tc_commit_elect(bar_acc + 8 * (t * 2));
                                 }
                                 used[S0] += 2; used[(S0 + 1) % RING] += 1; used[(S0 + 2) % RING] += 1;
                             };
@@ -295,7 +302,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             tc_commit_elect(bar_empty + 8 * slot);
                             ++it;
                         }
-                        tc_commit_elect(bar_acc + 8 * t);
+                        if (!st_uniform || st_xsync) tc_commit_elect(bar_acc + 8 * (t * 2));
+                        tc_commit_elect(bar_acc + 8 * (t * 2 + 1));
                         tr.log('C', tl, ss, t);
                     }
                 }
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         const int row = q * 32 + lane;                 // feature within a half (FiLM) / point (heads, input slots)
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
         unsigned char* tsm = smem + t * TILE_SMEM;
-        const uint32_t my_acc = bar_acc + 8 * t, my_aready = bar_aready + 8 * t;
+        const uint32_t my_acc = bar_acc + 16 * t, my_aready = bar_aready + 16 * t;     // + 8 * h
         const uint32_t my_xmain = bar_xmain + 8 * t, my_xready = bar_xready + 8 * t;
         const uint32_t xrow_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;   // K-major row of this point
         const uint32_t xsw = (uint32_t)(row & 7);
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(my_aready);
+            if (lane == 0) { mbar_arrive(my_aready); mbar_arrive(my_aready + 8); }
 
             for (int s = 0; s < a.n_stages; ++s) {
                 const StageOp sop = s_stages[s];
@@ -401,13 +409,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         if (lane == 0) mbar_arrive(my_xready);
                         ++n_x;
                     }
-                    mbar_wait(my_acc, n_acc & 1);
-                    ++n_acc;
-                    tc_fence_after();
-                    tr.log('W', tl, s, 0);
                     const uint32_t kk = (uint32_t)(fl & 63);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        mbar_wait(my_acc + 8 * h, n_acc & 1);
+                        tc_fence_after();
+                        if (h == 0) tr.log('W', tl, s, 0);
                         // feature f = h*128 + fl -> chunk f/64, row k = f%64 of the MN-major chunk
                         // [k/8][point/64][k%8][64 points]
                         unsigned char* rowp = tsm + (uint32_t)(h * 2 + (fl >> 6)) * CHUNK_BYTES + (kk >> 3) * 2048u + (kk & 7u) * 128u;
@@ -431,9 +438,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                 *reinterpret_cast<uint4*>(rowp + (pt8 >> 3) * 1024u + (((pt8 & 7u) ^ sw) << 4)) = pk;
                             }
                         }
+                        // chunks 2h, 2h+1 written, accumulator half h drained
+                        if (h == 0) tr.log('H', tl, s, 0);
+                        fence_async_smem();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(my_aready + 8 * h);
                     }
+                    ++n_acc;
                 } else {
                     mbar_wait(my_acc, n_acc & 1);
+                    mbar_wait(my_acc + 8, n_acc & 1);
                     ++n_acc;
                     tc_fence_after();
                     tr.log('W', tl, s, 0);
@@ -472,11 +487,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     }
                 }
                 tr.log('D', tl, s, 0);
-                if (!last) {
+                if (!last && sop.epi != EPI_FILM) {
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(my_aready);
+                    if (lane == 0) { mbar_arrive(my_aready); mbar_arrive(my_aready + 8); }
                 }
             }
         }
