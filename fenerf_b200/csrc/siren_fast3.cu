@@ -17,8 +17,8 @@
 //     bytes at a time; TMEM is drained in 16-column double-buffered pieces.
 //
 //   warps 0..2    weight producers (one per ring slot)
-//   warp  3       MMA issuer (warp-converged, elect.sync)
-//   warps 4..7    epilogue of tile X      warps 8..11   epilogue of tile Y
+//   warps 3, 4    MMA issuers of tile X / tile Y (warp-converged, elect.sync)
+//   warps 5..8    epilogue of tile X      warps 9..12   epilogue of tile Y
 #include "common.cuh"
 #include "siren_common.cuh"
 #include "tc5.cuh"
@@ -32,9 +32,9 @@ using namespace tc5;
 
 constexpr int TILE = 128;
 constexpr int RING = 3;
-constexpr int MMA_WARP = RING;
-constexpr int EPI_WARP0 = RING + 1;
-constexpr int NTHREADS = (EPI_WARP0 + 8) * 32;      // 384
+constexpr int MMA_WARP = RING;                       // issuer of tile X; MMA_WARP + 1 issues tile Y
+constexpr int EPI_WARP0 = RING + 2;
+constexpr int NTHREADS = (EPI_WARP0 + 8) * 32;      // 416
 constexpr uint32_t CHUNK_BYTES = 16384;
 constexpr uint32_t STAGE_BYTES = 32768;
 constexpr uint32_t TILE_SMEM = 4 * CHUNK_BYTES;      // four activation chunks per tile
@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = sbase + SMEM_BAR;             // [RING]
-    const uint32_t bar_empty = bar_full + 8 * RING;         // [RING]
+    const uint32_t bar_full = sbase + SMEM_BAR;             // [RING][2]: slot filled with a load of tile t (each issuer
+                                                            // only ever waits on its own tile's barriers, in order)
+    const uint32_t bar_empty = bar_full + 16 * RING;        // [RING]
     // Accumulator / operand hand-offs are per tile AND per feature half h (index t * 2 + h): half h of the
     // accumulator feeds activation chunks 2h, 2h+1 of the next layer, so the next layer's [h0 k01] MMAs can
     // start while the epilogue is still working on half 1, and the epilogue of half 0 starts while the
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     const uint32_t bar_aready = bar_acc + 32;               // [2][2] chunks 2h,2h+1 written + half h drained (epilogue t -> issuer)
     const uint32_t bar_xmain = bar_aready + 32;             // [2] colour layer 0: k01 MMAs retired, chunk 0 reusable
     const uint32_t bar_xready = bar_xmain + 16;             // [2] colour layer 0: extra input slots written into chunk 0
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (2 * RING + 12));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 8 * (3 * RING + 12));
 
     // The program tables are read once per load / stage by single threads on latency-critical paths
     // (producer turnaround, issuer phase changes): keep them in shared memory, not in the constant bank.
@@ -115,7 +116,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     for (int i = threadIdx.x; i < a.n_loads; i += NTHREADS) s_loads[i] = a.loads[i];
     for (int i = threadIdx.x; i < a.n_stages; i += NTHREADS) s_stages[i] = a.stages[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < RING; ++i) {
+            mbar_init(bar_full + 16 * i, 1); mbar_init(bar_full + 16 * i + 8, 1); mbar_init(bar_empty + 8 * i, 1);
+        }
         for (int t = 0; t < 2; ++t) {
             for (int h = 0; h < 2; ++h) {
                 mbar_init(bar_acc + 8 * (t * 2 + h), 1);
@@ -159,26 +162,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                 const unsigned char* src = a.packed + op.src;
                                 mbar_wait(bar_empty + 8 * warp, (uses & 1) ^ 1);
                                 ++uses;
-                                mbar_arrive_expect_tx(bar_full + 8 * warp, bytes);
-                                bulk_g2s(sbase + SMEM_RING + warp * STAGE_BYTES, src, bytes, bar_full + 8 * warp);
+                                mbar_arrive_expect_tx(bar_full + 16 * warp + 8 * t, bytes);
+                                bulk_g2s(sbase + SMEM_RING + warp * STAGE_BYTES, src, bytes, bar_full + 16 * warp + 8 * t);
                             }
                         }
                     s = s_end;
                 }
             }
         }
-    } else if (warp == MMA_WARP) {
-        // ================= MMA issuer (warp-converged; an elected lane issues) =================
-        uint32_t used[RING] = {0, 0, 0};            // per-slot use counts (phase parity)
+    } else if (warp == MMA_WARP || warp == MMA_WARP + 1) {
+        // ================= MMA issuers, one per tile (warp-converged; an elected lane issues) =================
+        // Both walk the same global load sequence (the ring order); each issues only its own tile's phases,
+        // so the ~1000 cycles of commit / barrier latency between two phases of one tile overlap with the
+        // other issuer's MMAs instead of idling the tensor pipe.
+        const int t = warp - MMA_WARP;
+        uint32_t used[RING] = {0, 0, 0};            // per-slot use counts of THIS tile (phase parity of full[slot][t])
         uint32_t it = 0;                            // global load number (slot = it % RING), as in the producers
-        uint32_t n_ready[2] = {0, 0}, n_x[2] = {0, 0};
-        Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, 1);
+        uint32_t n_ready = 0, n_x = 0;
+        Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, t == 0 ? 1 : 0);
         const uint32_t ring_lo = (sbase + SMEM_RING) >> 4;
         constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
         // one ring slot's "full" wait for a single-load step (slot number is a runtime value here)
         auto wait_full = [&](uint32_t slot) {
             const uint32_t cnt = slot == 0 ? used[0] : slot == 1 ? used[1] : used[2];
-            mbar_wait(bar_full + 8 * slot, cnt & 1);
+            mbar_wait(bar_full + 16 * slot + 8 * t, cnt & 1);
             tc_fence_after();
             if (slot == 0) ++used[0]; else if (slot == 1) ++used[1]; else ++used[2];
         };
@@ -195,12 +202,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
             for (int s = 0; s < a.n_stages;) {
                 int s_end = s + 1;
                 while ((m_fuse >> (s_end - 1)) & 1u) ++s_end;
-                for (int t = 0; t < nt; ++t) {
+                for (int tt = 0; tt < nt; ++tt) {
                     for (int ss = s; ss < s_end; ++ss) {
                         const bool st_uniform = (m_uniform >> ss) & 1u, st_xsync = (m_xsync >> ss) & 1u;
+                        if (tt != t) {                       // the other issuer's phase: only the ring position moves
+                            it += st_uniform ? (st_xsync ? 5u : 4u) : 1u;
+                            continue;
+                        }
                         tr.log('B', tl, ss, t);
-                        const uint32_t rdy_par = (t == 0 ? n_ready[0] : n_ready[1]) & 1;
-                        if (t == 0) ++n_ready[0]; else ++n_ready[1];
+                        const uint32_t rdy_par = n_ready & 1;
+                        ++n_ready;
                         mbar_wait(bar_aready + 8 * (t * 2), rdy_par);
                         // a plain FiLM layer observes half 1 only before its [h1 k01] round (inside `issue`)
                         if (!st_uniform) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             auto issue = [&](auto s0_tag) {
                                 constexpr int S0 = decltype(s0_tag)::value;
                                 constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);      // B (activations) MN-major
-                                mbar_wait(bar_full + 8 * S0, used[S0] & 1);
+                                mbar_wait(bar_full + 16 * S0 + 8 * t, used[S0] & 1);
                                 tc_fence_after();
 #pragma unroll
                                 for (int jj = 0; jj < 4; ++jj) {
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                         for (int k = 0; k < 4; ++k) {
                                             if (c == 1 && k == 0 && jj < 3) {   // next slot's wait overlaps this slot's MMAs
                                                 const int ns = (S0 + jj + 1) % RING;
-                                                mbar_wait(bar_full + 8 * ns, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
+                                                mbar_wait(bar_full + 16 * ns + 8 * t, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
                                                 // the [h1 k01] round needs accumulator half 1 drained (and, later, chunks 2,3)
                                                 if (jj == 0) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
                                                 tc_fence_after();
@@ -275,8 +286,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             it += 4;
                             if (st_xsync) {
                                 // wait until the epilogue has written the extra input slots into chunk 0
-                                mbar_wait(bar_xready + 8 * t, (t == 0 ? n_x[0] : n_x[1]) & 1);
-                                if (t == 0) ++n_x[0]; else ++n_x[1];
+                                mbar_wait(bar_xready + 8 * t, n_x & 1);
+                                ++n_x;
                                 tc_fence_after();
                                 tr.log('X', tl, ss, t);
                                 x_load(s_loads[s_stages[ss].l0 + 4]);
@@ -326,9 +337,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         const float* rgb_w = reinterpret_cast<const float*>(a.packed + L.rgb_w);
         const float* label_w = reinterpret_cast<const float*>(a.packed + L.label_w);
         uint32_t n_acc = 0, n_x = 0;
-        // traced: quadrant-0 warp of each tile (roles 2, 3) and the quadrant-3 warp of tile X (role 0; it shares
-        // its scheduler with the MMA issuer)
-        Tracer<kTrace> tr((q == 0 || (q == 3 && t == 0)) && lane == 0 ? a.trace : nullptr, q == 0 ? 2 + t : 0);
+        // traced: quadrant-0 warp of each tile (roles 2, 3); roles 1 / 0 are the issuers of tile X / Y
+        Tracer<kTrace> tr(q == 0 && lane == 0 ? a.trace : nullptr, 2 + t);
         int tl = 0;
         for (long long pair = blockIdx.x; pair * 2 + t < a.n_tiles; pair += gridDim.x, ++tl) {
             const long long tile = pair * 2 + t;

@@ -38,7 +38,7 @@ for role in range(4):
         ev.append((clk, role, chr(tag >> 48), (tag >> 32) & 0xffff, (tag >> 16) & 0xffff, tag & 0xffff))
 ev.sort()
 t0 = ev[0][0]
-names = ["epX3", "mma ", "epiX", "epiY"]
+names = ["mmaY", "mmaX", "epiX", "epiY"]
 for clk, role, kind, tile, stage, item in ev:
     if tile == show_tile:
         print("%9d %s %s tile%d stage%2d item%3d" % (clk - t0, names[role], kind, tile, stage, item))
