@@ -332,7 +332,7 @@ def field_roofline(gen, args, latents, md, device):
         origin, _, _ = vr.sample_camera_positions(device, n=B, horizontal_stddev=0.3, vertical_stddev=0.155, mode='gaussian')
         c2w = vr.create_cam2world_matrix(vr.normalize_vecs(-origin), origin, device=device).contiguous()
         durations = []
-        for it in range(4):
+        for it in range(6):
             pts, z, dirs, org = ops.ray_setup(rd, x_lin, y_lin, z_lin, c2w, torch.rand(B, N, S, 1, device=device))
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             # keep the GPU busy (~2 ms spin) while the host queues the launches below, so the events
@@ -348,7 +348,8 @@ def field_roofline(gen, args, latents, md, device):
             torch.cuda.synchronize()
             if it > 0:
                 durations += [e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])]
-    ms = sum(durations) / len(durations)
+    durations.sort()
+    ms = durations[len(durations) // 2] if len(durations) % 2 else 0.5 * (durations[len(durations) // 2 - 1] + durations[len(durations) // 2])
     flops = B * N * S * FLOP_PER_POINT[args.model]
     achieved = flops / (ms * 1e-3) / 1e12
     traffic = None

@@ -469,12 +469,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             tc_wait_ld();
                             if (valid) {
                                 const float inv_scale = __ldg(label_w + FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL);
+                                const float* lb = label_w + FENERF_MAX_LABEL * FN_H;
+                                float* orow = a.out + flat * C;
+                                // a point's row is 4C bytes: with an even C the label pairs go out as 8-byte stores
+                                const bool pair_ok = ((C & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 7) == 0);
 #pragma unroll
-                                for (int o = 0; o < 32; ++o) {
-                                    if (o < L.label_dim)
-                                        a.out[flat * C + o] = fmaf(__uint_as_float(r[o]), inv_scale, __ldg(label_w + FENERF_MAX_LABEL * FN_H + o));
-                                    else if (o == L.label_dim)
-                                        a.out[flat * C + (C - 1)] = __uint_as_float(r[o]) + __ldg(sigma_w + FN_H);
+                                for (int o = 0; o < 32; o += 2) {
+                                    const float v0 = fmaf(__uint_as_float(r[o]), inv_scale, __ldg(lb + o));
+                                    const float v1 = fmaf(__uint_as_float(r[o + 1]), inv_scale, __ldg(lb + o + 1));
+                                    if (o + 1 < L.label_dim && pair_ok) {
+                                        *reinterpret_cast<float2*>(orow + o) = make_float2(v0, v1);
+                                    } else {
+                                        if (o < L.label_dim) orow[o] = v0;
+                                        if (o + 1 < L.label_dim) orow[o + 1] = v1;
+                                    }
+                                    if (o == L.label_dim) orow[C - 1] = __uint_as_float(r[o]) + __ldg(sigma_w + FN_H);
+                                    if (o + 1 == L.label_dim) orow[C - 1] = __uint_as_float(r[o + 1]) + __ldg(sigma_w + FN_H);
                                 }
                             }
                         } else {
