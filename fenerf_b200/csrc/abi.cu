@@ -51,7 +51,8 @@ int check_render_desc(const fenerf_render_desc* rd) {
 }
 
 int run_field(const FnLayout& L, const void* packed, const float* points, const float* dirs, const float* film,
-              int batch, long long ppb, int dir_group, int lock_dirs, int precision, float* out, cudaStream_t st) {
+              int batch, long long ppb, int dir_group, int lock_dirs, int precision, float* out, cudaStream_t st,
+              int sigma_only = 0) {
     const unsigned char* pk = static_cast<const unsigned char*>(packed);
     if (precision == FENERF_PRECISION_EXACT)
         return siren_points_exact(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, nullptr, 0, out, st);
@@ -59,7 +60,7 @@ int run_field(const FnLayout& L, const void* packed, const float* points, const 
     // FENERF_B200_FAST_KERNEL=1 / 2 select the earlier ones for comparison
     static const int which = [] { const char* e = getenv("FENERF_B200_FAST_KERNEL"); return e ? atoi(e) : 3; }();
     if (which == 3)
-        return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), st);
+        return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), sigma_only, st);
     if (which == 2)
         return siren_points_fast2(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), st);
     return siren_points_fast(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, st);
@@ -98,6 +99,9 @@ int fenerf_siren_points(const fenerf_field_desc* field, const void* packed, cons
                         const float* film, int32_t batch, int64_t points_per_batch, int32_t dir_group,
                         int32_t precision, const int32_t* only_idx, int32_t n_only, float* out, void* stream) {
     FnLayout L;
+    const int sigma_only = (precision & FENERF_POINTS_SIGMA_ONLY) ? 1 : 0;
+    precision &= 0xff;
+    FN_REQUIRE(precision >= FENERF_PRECISION_EXACT && precision <= FENERF_PRECISION_GUARD, "unknown precision %d", precision);
     FN_REQUIRE(fn_make_layout(field, &L) == 0, "unsupported field description");
     FN_REQUIRE(packed && points && film && out, "NULL argument");
     FN_REQUIRE(dirs, "dirs is NULL (pass any (B,P/dir_group,3) tensor; the colour branch consumes it)");
@@ -110,7 +114,7 @@ int fenerf_siren_points(const fenerf_field_desc* field, const void* packed, cons
                                   0, only_idx, n_only, out, st);
     }
     FN_REQUIRE(precision >= FENERF_PRECISION_EXACT && precision <= FENERF_PRECISION_GUARD, "unknown precision %d", precision);
-    return run_field(L, packed, points, dirs, film, batch, points_per_batch, dir_group, 0, precision, out, st);
+    return run_field(L, packed, points, dirs, film, batch, points_per_batch, dir_group, 0, precision, out, st, sigma_only);
 }
 
 int fenerf_camera_poses(int32_t n, int32_t mode, float h_stddev, float v_stddev, float h_mean, float v_mean,

@@ -73,7 +73,7 @@ int siren_points_fast2(const FnLayout& L, const unsigned char* packed, const flo
                        long long* trace, cudaStream_t st);
 int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
-                       long long* trace, cudaStream_t st);
+                       long long* trace, int sigma_only, cudaStream_t st);
 int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                  const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
                  float* raw, int32_t* scratch_idx, cudaStream_t st);

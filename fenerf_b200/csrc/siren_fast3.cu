@@ -88,6 +88,7 @@ struct Fast3Args {
     long long ppb, tiles_per_batch, n_tiles;
     int dir_group, lock_dirs;
     int debug_short_loads;
+    int sigma_only;        // the program stops after the trunk head; only out[..., C-1] is written
     long long* trace;
 };
 
@@ -477,7 +478,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                 for (int o = 0; o < 32; o += 2) {
                                     const float v0 = fmaf(__uint_as_float(r[o]), inv_scale, __ldg(lb + o));
                                     const float v1 = fmaf(__uint_as_float(r[o + 1]), inv_scale, __ldg(lb + o + 1));
-                                    if (o + 1 < L.label_dim && pair_ok) {
+                                    if (a.sigma_only) {
+                                    } else if (o + 1 < L.label_dim && pair_ok) {
                                         *reinterpret_cast<float2*>(orow + o) = make_float2(v0, v1);
                                     } else {
                                         if (o < L.label_dim) orow[o] = v0;
@@ -548,7 +550,7 @@ void push_head(Fast3Args& A, size_t img_off, int img_rows, int n) {
     op->n8 = (uint8_t)(n / 8); op->half = 0; op->first = 1; op->w_is_a = 0;
 }
 
-bool build_program(const FnLayout& L, Fast3Args& A) {
+bool build_program(const FnLayout& L, Fast3Args& A, bool sigma_only) {
     A.n_loads = 0; A.n_stages = 0;
     auto end_stage = [&](uint8_t epi, uint8_t film, int l0) -> StageOp& {
         StageOp& st = A.stages[A.n_stages++];
@@ -567,7 +569,8 @@ bool build_program(const FnLayout& L, Fast3Args& A) {
             push_head(A, L.head_img, 32, L.label_dim > 0 ? 32 : 8);
             // the head and the first colour layer of a tile are issued back to back: the other tile is in
             // its long epilogue meanwhile, and would otherwise hold the in-order issuer at its own head
-            end_stage(EPI_HEAD_TRUNK, 0, l0).fuse_next = 1;
+            end_stage(EPI_HEAD_TRUNK, 0, l0).fuse_next = sigma_only ? 0 : 1;
+            if (sigma_only) return true;      // density only: the program ends at the trunk head
         }
         const bool c0 = (l == L.trunk_hidden);
         int l0 = A.n_loads;
@@ -593,14 +596,15 @@ bool build_program(const FnLayout& L, Fast3Args& A) {
 
 int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
-                       long long* trace, cudaStream_t st) {
+                       long long* trace, int sigma_only, cudaStream_t st) {
     static_assert(sizeof(Fast3Args) <= 4000, "kernel parameter block too large");
     static_assert(SMEM_TOTAL <= 232448, "one CTA per SM: 227 KB of shared memory");
     FN_REQUIRE(L.trunk_hidden >= 1 && L.n_hidden - L.trunk_hidden >= 1, "field needs >= 2 trunk and >= 1 colour layers");
     FN_REQUIRE(L.label_dim < 32, "the tcgen05 path packs labels and sigma into one 32-row head (label_dim <= 31)");
     Fast3Args a;
     memset(&a, 0, sizeof(a));
-    FN_REQUIRE(build_program(L, a), "field too deep for the stage program");
+    FN_REQUIRE(build_program(L, a, sigma_only != 0), "field too deep for the stage program");
+    a.sigma_only = sigma_only ? 1 : 0;
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out;
     a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
     a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs; a.trace = trace;

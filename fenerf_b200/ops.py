@@ -75,7 +75,22 @@ def make_render_desc(*, batch, img_size, num_steps, hierarchical, clamp_mode, ne
 # --------------------------------------------------------------------------------------------
 # point network
 # --------------------------------------------------------------------------------------------
-def siren_points(module, points, film, ray_directions, precision=None, dir_group=None, only_idx=None):
+POINTS_SIGMA_ONLY = 0x100     # FENERF_POINTS_SIGMA_ONLY
+
+
+def siren_sigma(module, points, film, precision=None):
+    """Density only: (B,P,3) points, (B,L,2,256) FiLM table -> (B,P,1).
+
+    What extract_double_semantic_shapes.py:59-62 keeps of the point network's output
+    (`coarse_output[:, :, -1:]` on a 256^3 grid); the colour and label branches are not evaluated.
+    """
+    b, p, _ = points.shape
+    dirs = torch.zeros((b, 1, 3), dtype=torch.float32, device=points.device)
+    out = siren_points(module, points, film, dirs, precision=precision, dir_group=p, _sigma_only=True)
+    return out[..., -1:]
+
+
+def siren_points(module, points, film, ray_directions, precision=None, dir_group=None, only_idx=None, _sigma_only=False):
     """(B,P,3) points, (B,L,2,256) FiLM table, (B,P,3) or (B,P/g,3) directions -> (B,P,C).
 
     The entry behind <SIREN>.forward_with_frequencies_phase_shifts (siren/siren.py:164-178,
@@ -109,7 +124,8 @@ def siren_points(module, points, film, ray_directions, precision=None, dir_group
     with torch.cuda.device(device):
         _lib.check(_lib.lib().fenerf_siren_points(
             C.byref(packed.desc), packed.ptr, _chk(pts, "points"), _chk(dirs, "ray_directions"), _chk(flm, "film"),
-            b, p, dir_group, _precision_code(precision), idx_ptr, n_only, _chk(out, "out"), _stream(device)))
+            b, p, dir_group, _precision_code(precision) | (POINTS_SIGMA_ONLY if _sigma_only else 0), idx_ptr, n_only,
+            _chk(out, "out"), _stream(device)))
     return out
 
 

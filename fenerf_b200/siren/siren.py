@@ -185,6 +185,13 @@ class _FieldBase(nn.Module):
         from .. import ops
         return ops.siren_points(self, points, film, ray_directions)
 
+    def density(self, points, film, precision=None):
+        """(B,P,3) points, (B,L,2,256) FiLM table (see film_table) -> (B,P,1) density only: what the shape
+        extraction keeps of forward_with_frequencies_phase_shifts (extract_double_semantic_shapes.py:59-62),
+        without evaluating the colour / label branches."""
+        from .. import ops
+        return ops.siren_sigma(self, points, film, precision)
+
 
 class TALLSIREN(_FieldBase):
     """pi-GAN's primary SIREN: 8 FiLM + sigma head + 1 colour FiLM + sigmoid rgb (model A)."""

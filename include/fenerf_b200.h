@@ -110,6 +110,11 @@ int fenerf_pack_field(const fenerf_field_desc* field, const fenerf_field_params*
  *   out     (B, P, C)
  *   only_idx  optional int32 list (n_only entries) of flat point indices b*P+p to evaluate;
  *             others are left untouched in `out` (used by the GUARD refinement)               */
+/* OR-ed into `precision`: only the density channel out[..., C-1] is required (a 256^3 density grid for
+ * marching cubes, extract_double_semantic_shapes.py:59-62 keeps `[:, :, -1:]`); the colour / label
+ * branches are skipped on the tcgen05 path and the other channels of `out` are then left unspecified. */
+#define FENERF_POINTS_SIGMA_ONLY 0x100
+
 int fenerf_siren_points(const fenerf_field_desc* field, const void* packed,
                         const float* points, const float* dirs, const float* film,
                         int32_t batch, int64_t points_per_batch, int32_t dir_group,
