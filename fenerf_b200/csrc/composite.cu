@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(kRaysPerBlock * 32) composite_kernel(Composite
             // NCHW store, *2-1: one 4-byte store per channel; the 8 warps of a block own 8 consecutive
             // pixels of each channel row, so a row's stores merge in L2
             __syncwarp();
-            const long long b = ray / A.rays_per_batch, p = ray % A.rays_per_batch;
+            // 32-bit index arithmetic (composite() checks n_rays < 2^31): a 64-bit division is ~150 instructions
+            const unsigned rpb = (unsigned)A.rays_per_batch;
+            const long long b = (unsigned)ray / rpb, p = (unsigned)ray % rpb;
             for (int c = lane; c < A.C_img; c += 32)
                 A.pixels[(b * A.C_img + c) * A.rays_per_batch + p] = __fsub_rn(__fmul_rn(s_out[c][warp], 2.f), 1.f);
             __syncwarp();
@@ -244,6 +246,7 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
     CompositeArgs A;
     A.rays_per_batch = (long long)rd->img_h * rd->img_w;
     A.n_rays = A.rays_per_batch * rd->batch;
+    FN_REQUIRE(A.n_rays < (1ll << 31), "too many rays for one launch: %lld", A.n_rays);
     A.S = rd->num_steps;
     A.n_samples = rd->hierarchical ? 2 * rd->num_steps : rd->num_steps;
     FN_REQUIRE(A.n_samples <= kMaxSamples && A.S >= 2, "num_steps %d unsupported (max %d per pass)", rd->num_steps,

@@ -26,10 +26,12 @@ ray_setup_kernel(int B, int H, int W, int S, float tan_half, const float* __rest
     const float dist = __fsub_rn(z_lin[1], z_lin[0]);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int s = (int)(idx % S);
-        long long ray = idx / S;
-        int b = (int)(ray / N);
-        int p = (int)(ray % N);
+        // 32-bit index arithmetic (ray_setup() checks total < 2^31)
+        const unsigned ui = (unsigned)idx;
+        int s = (int)(ui % (unsigned)S);
+        long long ray = ui / (unsigned)S;
+        int b = (int)((unsigned)ray / (unsigned)N);
+        int p = (int)((unsigned)ray % (unsigned)N);
         int row = p / W, col = p % W;
         float x = x_lin[col], y = y_lin[row];
         float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(zc, zc)));
@@ -135,6 +137,7 @@ int ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_l
               const float* cam2world, const float* rng_perturb, float* points, float* z_vals, float* dirs,
               float* origins, cudaStream_t st) {
     long long total = (long long)rd->batch * rd->img_h * rd->img_w * rd->num_steps;
+    FN_REQUIRE(total < (1ll << 31), "too many samples for one launch: %lld", total);
     int threads = 256;
     long long want = (total + threads - 1) / threads;
     int blocks = (int)(want < (long long)num_sms() * 16 ? want : (long long)num_sms() * 16);

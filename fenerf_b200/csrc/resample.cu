@@ -80,7 +80,7 @@ resample_kernel(long long n_rays, long long rays_per_batch, int S, int C, int cl
             cdf[i] = c;
         }
         __syncwarp();
-        const int b = (int)(ray / rays_per_batch);
+        const int b = (int)((unsigned)ray / (unsigned)rays_per_batch);     // n_rays < 2^31 (checked by the host)
         const float o0 = origins[b * 3 + 0], o1 = origins[b * 3 + 1], o2 = origins[b * 3 + 2];
         const float d0 = dirs[ray * 3 + 0], d1 = dirs[ray * 3 + 1], d2 = dirs[ray * 3 + 2];
         const int n_cdf = S - 1;
@@ -119,6 +119,7 @@ int resample(const fenerf_render_desc* rd, int C, const float* raw, const float*
                rd->num_steps, kMaxS);
     long long rpb = (long long)rd->img_h * rd->img_w;
     long long n_rays = rpb * rd->batch;
+    FN_REQUIRE(n_rays < (1ll << 31), "too many rays for one launch: %lld", n_rays);
     long long want = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int blocks = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
     if (blocks < 1) blocks = 1;
