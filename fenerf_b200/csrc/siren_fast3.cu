@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     split_f16(dir[i], hi, lo);
                     slots[FN_SLOT_DIR + i] = hi; slots[FN_SLOT_DIR + 3 + i] = lo; slots[FN_SLOT_DIR + 6 + i] = hi;
                 }
-                if (L.grid_channels > 0 && valid) {
+                if (L.grid_channels > 0 && valid && !a.sigma_only) {     // density needs no grid features
                     float feat[32];
                     grid_features32(reinterpret_cast<const float*>(a.packed + L.grid), L.grid_res, pos[0], pos[1], pos[2], feat);
 #pragma unroll
