@@ -56,14 +56,9 @@ int run_field(const FnLayout& L, const void* packed, const float* points, const 
     const unsigned char* pk = static_cast<const unsigned char*>(packed);
     if (precision == FENERF_PRECISION_EXACT)
         return siren_points_exact(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, nullptr, 0, out, st);
-    // three generations of the tcgen05 kernel; the third is the default,
-    // FENERF_B200_FAST_KERNEL=1 / 2 select the earlier ones for comparison
-    static const int which = [] { const char* e = getenv("FENERF_B200_FAST_KERNEL"); return e ? atoi(e) : 3; }();
-    if (which == 3)
-        return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), sigma_only, st);
-    if (which == 2)
-        return siren_points_fast2(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), st);
-    return siren_points_fast(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, st);
+    // the tcgen05 kernel (siren_fast3.cu: third generation; its predecessors are described in DESIGN.md
+    // section 5 and live in the history only)
+    return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), sigma_only, st);
 }
 
 }  // namespace

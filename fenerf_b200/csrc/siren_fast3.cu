@@ -1,6 +1,6 @@
-// Point network, FAST mode, third-generation kernel: two anti-phased tiles, three 32 KB ring slots.
+// Point network, FAST mode (tcgen05), third-generation kernel: two tiles per CTA, three 32 KB ring slots.
 //
-// Same math as siren_fast.cu / siren_fast2.cu.  What the measurements of round 1 say
+// What the measurements of round 1 say
 // (profiles/r01_*.txt): per 128-point layer-tile the tensor pipe, the MUFU pipe
 // and the TMEM->register path each need ~2048 cycles, a layer is a dependency chain
 // MMA -> epilogue -> MMA, a ring slot's turnaround is ~1800 cycles whatever its size, and the MMA
@@ -592,7 +592,13 @@ bool build_program(const FnLayout& L, Fast3Args& A, bool sigma_only) {
     return true;
 }
 
+long long* g_trace = nullptr;
+
 }  // namespace
+
+// fenerf_debug_trace: device buffer (4 roles x 4096 int64) that CTA 0 of the next launches logs into, or NULL
+void set_fast_trace(long long* buf) { g_trace = buf; }
+long long* get_fast_trace() { return g_trace; }
 
 int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
