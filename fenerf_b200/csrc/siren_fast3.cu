@@ -341,6 +341,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         // traced: quadrant-0 warp of each tile (roles 2, 3); roles 1 / 0 are the issuers of tile X / Y
         Tracer<kTrace> tr(q == 0 && lane == 0 ? a.trace : nullptr, 2 + t);
         int tl = 0;
+        // position (already box-warped) and view direction of this thread's point in tile `tile_i`; zeros past the end
+        auto load_inputs = [&](long long tile_i, float (&pos)[3], float (&dir)[3]) {
+            const long long bb = tile_i / a.tiles_per_batch;
+            const long long pp = (tile_i % a.tiles_per_batch) * TILE + row;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { pos[i] = 0.f; dir[i] = 0.f; }
+            if (pp < a.ppb) {
+                const long long ff = bb * a.ppb + pp;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pos[i] = __fmul_rn(a.points[ff * 3 + i], L.input_scale);
+                if (a.lock_dirs) dir[2] = -1.f;
+                else {
+                    const long long di = bb * (a.ppb / a.dir_group) + pp / a.dir_group;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) dir[i] = a.dirs[di * 3 + i];
+                }
+            }
+        };
+        float next_pos[3], next_dir[3];      // fetched during the previous tile's last stage (off the tile-start path)
+        bool have_next = false;
         for (long long pair = blockIdx.x; pair * 2 + t < a.n_tiles; pair += gridDim.x, ++tl) {
             const long long tile = pair * 2 + t;
             const long long b = tile / a.tiles_per_batch;
@@ -352,16 +372,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
             //      features kept in registers until the first colour layer ----
             uint4 xslots[8];
             {
-                float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
-                if (valid) {
+                float pos[3], dir[3];
+                if (have_next) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) pos[i] = __fmul_rn(a.points[flat * 3 + i], L.input_scale);
-                    if (a.lock_dirs) dir[2] = -1.f;
-                    else {
-                        const long long di = b * (a.ppb / a.dir_group) + pnt / a.dir_group;
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) dir[i] = a.dirs[di * 3 + i];
-                    }
+                    for (int i = 0; i < 3; ++i) { pos[i] = next_pos[i]; dir[i] = next_dir[i]; }
+                } else {
+                    load_inputs(tile, pos, dir);
                 }
                 __align__(16) __half slots[64];
 #pragma unroll
@@ -458,6 +474,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     }
                     ++n_acc;
                 } else {
+                    if (last) {
+                        // the inputs of this thread's next point: requested now, consumed at the next tile start
+                        const long long ntile = (pair + gridDim.x) * 2 + t;
+                        have_next = ntile < a.n_tiles;
+                        if (have_next) load_inputs(ntile, next_pos, next_dir);
+                    }
                     mbar_wait(my_acc, n_acc & 1);
                     mbar_wait(my_acc + 8, n_acc & 1);
                     ++n_acc;
@@ -622,7 +644,11 @@ int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const flo
     FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);
     const long long n_pairs = (a.n_tiles + 1) / 2;
     auto kernel = a.trace ? siren_fast3_kernel<true> : siren_fast3_kernel<false>;
-    FN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    static bool attr_set[2] = {false, false};              // once per kernel instantiation
+    if (!attr_set[a.trace ? 1 : 0]) {
+        FN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+        attr_set[a.trace ? 1 : 0] = true;
+    }
     int blocks = (int)(n_pairs < (long long)num_sms() ? n_pairs : (long long)num_sms());
     kernel<<<blocks, NTHREADS, SMEM_TOTAL, st>>>(a);
     FN_LAUNCH_OK("siren_fast3_kernel");
