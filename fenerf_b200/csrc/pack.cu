@@ -91,6 +91,11 @@ __global__ void label_step1_kernel(const float* __restrict__ w3, const float* __
                                    const float* __restrict__ w2, const float* __restrict__ b2,
                                    double* __restrict__ u /*[L][257]*/) {
     int i = blockIdx.x, j = threadIdx.x;
+    if (!w2) {                      // two-layer chain (siren.py:1189-1191): the middle layer is the identity
+        u[i * (FN_H + 1) + j] = (double)w3[i * FN_H + j];
+        if (j == 0) u[i * (FN_H + 1) + FN_H] = (double)b3[i];
+        return;
+    }
     double acc = 0.0;
     for (int m = 0; m < FN_H; ++m) acc += (double)w3[i * FN_H + m] * (double)w2[m * FN_H + j];
     u[i * (FN_H + 1) + j] = acc;
@@ -206,7 +211,8 @@ int pack_field(const fenerf_field_desc* f, const FnLayout& L, const fenerf_field
                                          (float*)(packed + L.rgb_w));
     FN_LAUNCH_OK("pack_heads_kernel");
     if (L.label_dim > 0) {
-        for (int i = 0; i < 3; ++i) FN_REQUIRE(p->label_w[i] && p->label_b[i], "label layer %d missing", i);
+        for (int i = 0; i < 3; i += 2) FN_REQUIRE(p->label_w[i] && p->label_b[i], "label layer %d missing", i);
+        FN_REQUIRE((p->label_w[1] == nullptr) == (p->label_b[1] == nullptr), "label layer 1: weight and bias must both be given or both be NULL");
         double* u = reinterpret_cast<double*>(packed + L.label_scratch);
         label_step1_kernel<<<L.label_dim, FN_H, 0, st>>>(p->label_w[2], p->label_b[2], p->label_w[1], p->label_b[1], u);
         FN_LAUNCH_OK("label_step1_kernel");

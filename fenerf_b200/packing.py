@@ -59,9 +59,16 @@ def collect_params(module, device):
     p.rgb_w = ptr(module.color_layer_linear[0].weight)
     p.rgb_b = ptr(module.color_layer_linear[0].bias)
     if spec.label_dim:
-        for i in range(3):
-            p.label_w[i] = ptr(module.label_layer_linear[i].weight)
-            p.label_b[i] = ptr(module.label_layer_linear[i].bias)
+        chain = [m for m in module.label_layer_linear if isinstance(m, torch.nn.Linear)]
+        if len(chain) not in (2, 3):
+            raise ValueError("label head: expected a chain of 2 or 3 Linear layers, got %d" % len(chain))
+        # slots: [first 256->256, middle 256->256 or absent, last 256->label_dim]
+        slots = {0: chain[0], 2: chain[-1]}
+        if len(chain) == 3:
+            slots[1] = chain[1]
+        for i, lin in slots.items():
+            p.label_w[i] = ptr(lin.weight)
+            p.label_b[i] = ptr(lin.bias)
     if spec.grid_channels:
         p.grid = ptr(module.spatial_embeddings)
     return p, keep

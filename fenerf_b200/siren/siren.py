@@ -15,6 +15,8 @@ Reference interfaces mirrored (file:line under /root/reference):
   TALLSIREN                                   siren/siren.py:126-178
   UniformBoxWarp                              siren/siren.py:181-187
   sample_from_3dgrid                          siren/siren.py:314-330
+  SPATIALSIRENBASELINE                        siren/siren.py:189-244
+  SIRENBASELINESEMANTICDISENTANGLE            siren/siren.py:1163-1229
   TextureEmbeddingPiGAN128SEMANTICDISENTANGLE siren/siren.py:1451-1530
   ...256SEMANTICDISENTANGLE / ..._DIM_96      siren/siren.py:1533-1546
 """
@@ -234,7 +236,95 @@ class TALLSIREN(_FieldBase):
         return self._render_points(input, self.film_table(frequencies, phase_shifts), ray_directions)
 
 
-class TextureEmbeddingPiGAN128SEMANTICDISENTANGLE(_FieldBase):
+class SPATIALSIRENBASELINE(TALLSIREN):
+    """TALLSIREN plus a UniformBoxWarp(0.24) on the input points (siren/siren.py:189-244); the network of the
+    `CelebA` curriculum (curriculums.py:66)."""
+
+    def __init__(self, input_dim=2, z_dim=100, hidden_dim=256, output_dim=1, device=None):
+        nn.Module.__init__(self)
+        self.device = device
+        self.input_dim = input_dim
+        self.z_dim = z_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+
+        widths = [3] + [hidden_dim] * 8
+        self.network = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        self.final_layer = nn.Linear(hidden_dim, 1)
+        self.color_layer_sine = FiLMLayer(hidden_dim + 3, hidden_dim)
+        self.color_layer_linear = nn.Sequential(nn.Linear(hidden_dim, 3))
+        self.mapping_network = CustomMappingNetwork(z_dim, 256, (len(self.network) + 1) * hidden_dim * 2)
+
+        for part in (self.network, self.final_layer, self.color_layer_sine, self.color_layer_linear):
+            part.apply(frequency_init(25))
+        self.network[0].apply(first_layer_film_sine_init)
+        self.gridwarper = UniformBoxWarp(0.24)
+
+    def field_spec(self):
+        return FieldSpec(trunk_layers=len(self.network), color_layers=1, label_dim=0, grid_channels=0,
+                         grid_res=0, input_scale=float(self.gridwarper.scale_factor), out_dim=4, double_latent=False)
+
+
+class _DoubleLatentField(_FieldBase):
+    """forward / FiLM-table plumbing shared by the double-latent (geometry, appearance) fields."""
+
+    def film_table(self, frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app):
+        """-> (B, L_geo + L_app, 2, 256) [15 f + 30, phase], geometry layers first (siren.py:1510-1511)."""
+        b = frequencies_geo.shape[0]
+        h = self.hidden_dim
+        f = torch.cat([(frequencies_geo * 15 + 30).reshape(b, -1, h), (frequencies_app * 15 + 30).reshape(b, -1, h)], 1)
+        p = torch.cat([phase_shifts_geo.reshape(b, -1, h), phase_shifts_app.reshape(b, -1, h)], 1)
+        return torch.stack([f, p], dim=2).float().contiguous()
+
+    def forward(self, input, z_geo, z_app, ray_directions, **kwargs):
+        frequencies_geo, phase_shifts_geo = self.geo_mapping_network(z_geo)
+        frequencies_app, phase_shifts_app = self.app_mapping_network(z_app)
+        return self.forward_with_frequencies_phase_shifts(
+            input, frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app, ray_directions, **kwargs)
+
+    def forward_with_frequencies_phase_shifts(self, input, frequencies_geo, frequencies_app, phase_shifts_geo,
+                                              phase_shifts_app, ray_directions, **kwargs):
+        film = self.film_table(frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app)
+        return self._render_points(input, film, ray_directions)
+
+
+class SIRENBASELINESEMANTICDISENTANGLE(_DoubleLatentField):
+    """TALLSIREN-style trunk with two latent codes and semantic logits, no feature grid
+    (siren/siren.py:1163-1229); the network of the `CelebA_double_semantic` curriculum (curriculums.py:111).
+    Output channels: [labels (output_dim-4), rgb (3), sigma (1)]; the label head is a two-Linear chain."""
+
+    def __init__(self, input_dim=2, z_geo_dim=100, z_app_dim=100, hidden_dim=256, output_dim=1, device=None):
+        super().__init__()
+        self.device = device
+        self.input_dim = input_dim
+        self.z_geo_dim = z_geo_dim
+        self.z_app_dim = z_app_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+
+        widths = [3] + [hidden_dim] * 8
+        self.network = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        self.final_layer = nn.Linear(hidden_dim, 1)
+        cwidths = [hidden_dim + 3] + [hidden_dim] * 3
+        self.color_layer_sine = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(cwidths[:-1], cwidths[1:]))
+        self.color_layer_linear = nn.Sequential(nn.Linear(hidden_dim, 3))
+        self.geo_mapping_network = CustomMappingNetwork(z_geo_dim, 256, len(self.network) * hidden_dim * 2)
+        self.app_mapping_network = CustomMappingNetwork(z_app_dim, 256, len(self.color_layer_sine) * hidden_dim * 2)
+        self.label_layer_linear = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.Linear(hidden_dim, self.output_dim - 4))
+
+        for part in (self.network, self.final_layer, self.color_layer_sine, self.color_layer_linear,
+                     self.label_layer_linear):
+            part.apply(frequency_init(25))
+        self.network[0].apply(first_layer_film_sine_init)
+        self.gridwarper = UniformBoxWarp(0.24)
+
+    def field_spec(self):
+        return FieldSpec(trunk_layers=len(self.network), color_layers=len(self.color_layer_sine),
+                         label_dim=self.output_dim - 4, grid_channels=0, grid_res=0,
+                         input_scale=float(self.gridwarper.scale_factor), out_dim=self.output_dim, double_latent=True)
+
+
+class TextureEmbeddingPiGAN128SEMANTICDISENTANGLE(_DoubleLatentField):
     """Double-latent field: geometry trunk + semantic head, texture branch with a 3-D feature grid
     (model B).  Output channels: [labels (output_dim-4), rgb (3), sigma (1)]."""
 
@@ -274,25 +364,6 @@ class TextureEmbeddingPiGAN128SEMANTICDISENTANGLE(_FieldBase):
                          label_dim=self.output_dim - 4, grid_channels=g.shape[1], grid_res=g.shape[2],
                          input_scale=float(self.gridwarper.scale_factor), out_dim=self.output_dim,
                          double_latent=True)
-
-    def film_table(self, frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app):
-        """-> (B, L_geo + L_app, 2, 256) [15 f + 30, phase], geometry layers first (siren.py:1510-1511)."""
-        b = frequencies_geo.shape[0]
-        h = self.hidden_dim
-        f = torch.cat([(frequencies_geo * 15 + 30).reshape(b, -1, h), (frequencies_app * 15 + 30).reshape(b, -1, h)], 1)
-        p = torch.cat([phase_shifts_geo.reshape(b, -1, h), phase_shifts_app.reshape(b, -1, h)], 1)
-        return torch.stack([f, p], dim=2).float().contiguous()
-
-    def forward(self, input, z_geo, z_app, ray_directions, **kwargs):
-        frequencies_geo, phase_shifts_geo = self.geo_mapping_network(z_geo)
-        frequencies_app, phase_shifts_app = self.app_mapping_network(z_app)
-        return self.forward_with_frequencies_phase_shifts(
-            input, frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app, ray_directions, **kwargs)
-
-    def forward_with_frequencies_phase_shifts(self, input, frequencies_geo, frequencies_app, phase_shifts_geo,
-                                              phase_shifts_app, ray_directions, **kwargs):
-        film = self.film_table(frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app)
-        return self._render_points(input, film, ray_directions)
 
 
 class TextureEmbeddingPiGAN256SEMANTICDISENTANGLE(TextureEmbeddingPiGAN128SEMANTICDISENTANGLE):

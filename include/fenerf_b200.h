@@ -79,7 +79,8 @@ typedef struct fenerf_field_params {
     const float* color_b[FENERF_MAX_COLOR];
     const float* rgb_w;                      /* [3][256] */
     const float* rgb_b;                      /* [3] */
-    const float* label_w[3];                 /* [256][256], [256][256], [label_dim][256]; NULL if label_dim == 0 */
+    const float* label_w[3];                 /* [256][256], [256][256], [label_dim][256]; NULL if label_dim == 0;
+                                                label_w[1] / label_b[1] NULL for a two-layer chain (siren.py:1189-1191) */
     const float* label_b[3];
     const float* grid;                       /* (1, G, R, R, R) or NULL */
 } fenerf_field_params;

@@ -144,26 +144,26 @@ def field_eval(field, points, film, dirs):
     """(B,P,3), (B,L,2,256) [15f+30, phase], (B,P,3) -> (B,P,C).  `field` is any module with the
     reference's attribute names (network, final_layer, color_layer_sine, ...)."""
     has_grid = hasattr(field, 'spatial_embeddings')
+    has_labels = hasattr(field, 'label_layer_linear')
     x = points
+    if hasattr(field, 'gridwarper'):
+        x = x * (2 / 0.24)                      # UniformBoxWarp(0.24), siren.py:218, 1203, 1501, 1513
     if has_grid:
-        x = x * (2 / 0.24)                      # UniformBoxWarp(0.24), siren.py:1501, 1513
         feats = grid_lookup(x, field.spatial_embeddings)
     h = x
     n_trunk = len(field.network)
     for i, layer in enumerate(field.network):
         h = _film(layer.layer, h, film[:, i, 0], film[:, i, 1])
     sigma = field.final_layer(h)
-    if has_grid:
-        c = torch.cat([dirs, feats, h], dim=-1)
+    c = torch.cat([dirs, feats, h], dim=-1) if has_grid else torch.cat([dirs, h], dim=-1)
+    if has_labels:
         labels = field.label_layer_linear(h)
-    else:
-        c = torch.cat([dirs, h], dim=-1)
     color = field.color_layer_sine
     color = list(color) if isinstance(color, torch.nn.ModuleList) else [color]
     for j, layer in enumerate(color):
         c = _film(layer.layer, c, film[:, n_trunk + j, 0], film[:, n_trunk + j, 1])
     rgb = torch.sigmoid(field.color_layer_linear[0](c))
-    return torch.cat([labels, rgb, sigma], dim=-1) if has_grid else torch.cat([rgb, sigma], dim=-1)
+    return torch.cat([labels, rgb, sigma], dim=-1) if has_labels else torch.cat([rgb, sigma], dim=-1)
 
 
 # --------------------------------------------------------------------------------------------

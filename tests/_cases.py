@@ -16,10 +16,33 @@ BASE = dict(fov=12, ray_start=0.88, ray_end=1.12, h_mean=math.pi * 0.5, v_mean=m
             last_back=False, hierarchical_sample=True, sample_dist='gaussian')
 
 
+#: model letter -> (generator class, SIREN class, number of latent codes, output_dim); A / B are the two
+#: benchmarked fields, C / D the networks of the reference's other two curricula (curriculums.py:66, 111)
+MODELS = {
+    "A": ("ImplicitGenerator3d", "TALLSIREN", 1, 4),
+    "B": ("DoubleImplicitGenerator3d", "TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96", 2, 22),
+    "C": ("ImplicitGenerator3d", "SPATIALSIRENBASELINE", 1, 4),
+    "D": ("DoubleImplicitGenerator3d", "SIRENBASELINESEMANTICDISENTANGLE", 2, 22),
+}
+
+
+def n_latents(model):
+    return MODELS[model][2]
+
+
+def construct(generators_mod, siren_mod, model, softmax_label=False):
+    """Generator of `model` from a (generators, siren) module pair -- the reference's or the mirror's."""
+    gen_name, siren_name, n_lat, out_dim = MODELS[model]
+    gen_cls, siren_cls = getattr(generators_mod, gen_name), getattr(siren_mod, siren_name)
+    if n_lat == 1:
+        return gen_cls(siren_cls, 256, out_dim, softmax_label=softmax_label)
+    return gen_cls(siren_cls, 256, 256, out_dim, softmax_label=softmax_label)
+
+
 @dataclass(frozen=True)
 class Case:
     name: str
-    model: str                     # "A" = ImplicitGenerator3d + TALLSIREN, "B" = Double + TexEmb_DIM_96
+    model: str                     # key of MODELS
     batch: int
     seed: int
     cfg: dict = field(default_factory=dict)
@@ -53,6 +76,10 @@ CASES = [
     Case("b_staged_segpad", "B", 1, 23, _cfg(img_size=16, num_steps=12, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
                                              fill_mode='seg_padding_background', fill_color='grey'),
          method="staged_forward", psi=0.7),
+    Case("c_small", "C", 2, 31, _cfg(img_size=16, num_steps=12, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("d_small", "D", 1, 32, _cfg(img_size=16, num_steps=12, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("d_staged_softmax", "D", 1, 33, _cfg(img_size=12, num_steps=10, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                              softmax_label=True, fill_mode='weight'), method="staged_forward", psi=0.7),
 ]
 CASE_BY_NAME = {c.name: c for c in CASES}
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -73,7 +100,7 @@ def make_latents(case):
     zs = []
     for i in range(case.batch):
         torch.manual_seed(1000 + i)
-        zs.append([torch.randn(1, 256) for _ in range(1 if case.model == "A" else 2)])
+        zs.append([torch.randn(1, 256) for _ in range(n_latents(case.model))])
     return tuple(torch.cat([z[j] for z in zs], 0) for j in range(len(zs[0])))
 
 
@@ -85,16 +112,12 @@ def reference_kwargs(case):
     return kw
 
 
-@lru_cache(maxsize=2)
+@lru_cache(maxsize=8)
 def _mirror_generator_cached(model, softmax_label):
     from fenerf_b200.generators import generators as g
     from fenerf_b200.siren import siren as s
     torch.manual_seed(0)
-    if model == "A":
-        gen = g.ImplicitGenerator3d(s.TALLSIREN, 256, 4, softmax_label=softmax_label)
-    else:
-        gen = g.DoubleImplicitGenerator3d(s.TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96, 256, 256, 22,
-                                          softmax_label=softmax_label)
+    gen = construct(g, s, model, softmax_label)
     gen.eval()
     return gen
 
@@ -113,4 +136,4 @@ def build_mirror(case, device="cpu"):
 
 def avg_film_draws(case):
     """The generate_avg_frequencies draws a staged_forward makes first (generators.py:142, 554)."""
-    return [torch.randn(10000, 256) for _ in range(1 if case.model == "A" else 2)]
+    return [torch.randn(10000, 256) for _ in range(n_latents(case.model))]

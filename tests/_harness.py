@@ -28,7 +28,7 @@ def oracle_run(case, gen=None, keep_stages=True):
             # parameters (generators.py:142-149, 554-564); equivalent in table form because
             # 15 (a + psi (f - a)) + 30 is evaluated from the truncated raw frequency
             avg_draws = _cases.avg_film_draws(case)
-            if case.model == "A":
+            if _cases.n_latents(case.model) == 1:
                 f, p = gen.siren.mapping_network(latents[0])
                 fa, pa = gen.siren.mapping_network(avg_draws[0])
                 fa, pa = fa.mean(0, keepdim=True), pa.mean(0, keepdim=True)

@@ -38,12 +38,7 @@ def state_digest(module):
 
 def build_reference(case, ref_generators, ref_siren):
     torch.manual_seed(0)
-    if case.model == "A":
-        gen = ref_generators.ImplicitGenerator3d(ref_siren.TALLSIREN, 256, 4, softmax_label=case.cfg.get("softmax_label", False))
-    else:
-        gen = ref_generators.DoubleImplicitGenerator3d(
-            ref_siren.TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96, 256, 256, 22,
-            softmax_label=case.cfg.get("softmax_label", False))
+    gen = _cases.construct(ref_generators, ref_siren, case.model, case.cfg.get("softmax_label", False))
     gen.set_device("cpu")
     gen.eval()
     digest = state_digest(gen)
@@ -54,7 +49,10 @@ def build_reference(case, ref_generators, ref_siren):
 def main():
     ref_generators, ref_siren, _ = ref_shim.load()
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    only = set(sys.argv[1:])                       # optional: case names to (re)generate
     for case in _cases.CASES:
+        if only and case.name not in only:
+            continue
         gen, digest = build_reference(case, ref_generators, ref_siren)
         latents = _cases.make_latents(case)
         kw = _cases.reference_kwargs(case)

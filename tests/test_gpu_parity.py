@@ -80,7 +80,7 @@ def test_ray_setup_stage(runs, name):
     assert (org.cpu() - st["origins"]).abs().max() <= 2e-6
 
 
-@pytest.mark.parametrize("name", ["a_small", "b_small", "b_small_opaque"])
+@pytest.mark.parametrize("name", ["a_small", "b_small", "b_small_opaque", "c_small", "d_small"])
 def test_field_exact_stage(runs, name):
     case, run = runs(name)
     st = run["out"]["stages"]
@@ -93,7 +93,7 @@ def test_field_exact_stage(runs, name):
     assert err.max() <= 5e-5, "max|field - oracle| = %g (per channel %s)" % (err.max(), err.amax((0, 1, 2)))
 
 
-@pytest.mark.parametrize("name", ["a_small", "b_small", "b_small_opaque"])
+@pytest.mark.parametrize("name", ["a_small", "b_small", "b_small_opaque", "c_small", "d_small"])
 def test_field_fast_stage(runs, name):
     """tcgen05 path vs oracle on the raw field outputs: fp16 operand rounding through 9-11 FiLM
     layers (gain ~1 per layer) stays at the few-1e-4 level (hard part 1)."""

@@ -73,14 +73,14 @@ def test_struct_sizes_match_the_c_header():
     assert sizes == [ctypes.sizeof(_lib.FieldDesc), ctypes.sizeof(_lib.FieldParams), ctypes.sizeof(_lib.RenderDesc)]
 
 
-@pytest.mark.parametrize("name", ["a_small", "b_small"])
+@pytest.mark.parametrize("name", ["a_small", "b_small", "c_small", "d_small"])
 def test_film_table_matches_oracle(name):
     case = _cases.CASE_BY_NAME[name]
     gen = _cases.build_mirror(case)
     lat = _cases.make_latents(case)
     want = oracle.film_from_latents(gen.siren, lat)
     with torch.no_grad():
-        if case.model == "A":
+        if _cases.n_latents(case.model) == 1:
             got = gen.siren.film_table(*gen.siren.mapping_network(lat[0]))
         else:
             fg, pg = gen.siren.geo_mapping_network(lat[0])

@@ -11,7 +11,7 @@ from oracle import ref_shim
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
 
 
-@pytest.mark.parametrize("name", ["a_small", "a_small_noise", "a_nohier_softplus", "a_lockview_uniform", "b_small"])
+@pytest.mark.parametrize("name", ["a_small", "a_small_noise", "a_nohier_softplus", "a_lockview_uniform", "b_small", "c_small", "d_small"])
 def test_oracle_is_bit_exact_with_reference(name):
     import sys
     sys.path.insert(0, _cases.GOLDEN_DIR)
