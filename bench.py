@@ -198,7 +198,7 @@ def run_reference_arm(args, world, rank):
         "e2e": {"value": value, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -316,7 +316,7 @@ def run_ours(args, world, rank, local):
     if world == 1 and not args.no_cpu_baseline:
         v, sample, cores = cpu_faces_per_sec(args.model, 1, 0, budget_s=40.0)
         line["cpu_baseline"] = {"value": v, "unit": "faces/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def field_roofline(gen, args, latents, md, device):
@@ -376,7 +376,29 @@ def field_roofline(gen, args, latents, md, device):
             "frac_of_burst_peak": achieved / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None}
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries underneath write there too (NCCL's version banner,
+    whatever the box's NCCL_DEBUG is), so the real stdout is kept aside and fd 1 points at stderr until
+    `emit` writes the line."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
