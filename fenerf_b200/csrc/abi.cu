@@ -55,7 +55,7 @@ int run_field(const FnLayout& L, const void* packed, const float* points, const 
               int sigma_only = 0) {
     const unsigned char* pk = static_cast<const unsigned char*>(packed);
     if (precision == FENERF_PRECISION_EXACT)
-        return siren_points_exact(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, nullptr, 0, out, st);
+        return siren_points_exact(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, nullptr, 0, out, st, sigma_only);
     // the tcgen05 kernel (siren_fast3.cu: third generation; its predecessors are described in DESIGN.md
     // section 5 and live in the history only)
     return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), sigma_only, st);

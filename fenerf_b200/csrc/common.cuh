@@ -62,7 +62,7 @@ int pack_field(const fenerf_field_desc* f, const FnLayout& L, const fenerf_field
                cudaStream_t st);
 int siren_points_exact(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs,
-                       const int32_t* only_idx, int n_only, float* out, cudaStream_t st);
+                       const int32_t* only_idx, int n_only, float* out, cudaStream_t st, int sigma_only = 0);
 void set_fast_trace(long long* buf);
 long long* get_fast_trace();
 int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,

@@ -42,6 +42,7 @@ struct ExactArgs {
     int n_only;
     int dir_group;
     int lock_dirs;
+    int sigma_only;      // stop after the density head: out[..., C-1] only (GUARD refinement, density grids)
 };
 
 // P = points per thread (4: dense 64-point tiles; 1: 16-point tiles for the sparse GUARD gather, where
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
         }
         for (int i = tid; i < (KA - FN_H - 3) * TM; i += NTHREADS) s.A[FN_H + 3 + i / TM][i % TM] = 0.f;
         __syncthreads();
-        if (L.grid_channels > 0) {
+        if (L.grid_channels > 0 && !a.sigma_only) {
             const float* grid = reinterpret_cast<const float*>(pk + L.grid);
             const int G = L.grid_channels;
             for (int it = tid; it < TM * G; it += NTHREADS) {
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
                 // heads on the trunk output: sigma, then the pre-multiplied label map
                 const float* sw = reinterpret_cast<const float*>(pk + L.sigma_w);
                 const float* lw = reinterpret_cast<const float*>(pk + L.label_w);
-                for (int it = tid; it < TM * (1 + L.label_dim); it += NTHREADS) {
+                for (int it = tid; it < TM * (1 + (a.sigma_only ? 0 : L.label_dim)); it += NTHREADS) {
                     int pt = it % TM, o = it / TM;
                     const float* w = o == 0 ? sw : lw + (size_t)(o - 1) * FN_H;
                     float r = o == 0 ? __ldg(sw + FN_H) : __ldg(lw + FENERF_MAX_LABEL * FN_H + (o - 1));
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
                     if (flat >= 0) a.out[flat * C + (o == 0 ? C - 1 : o - 1)] = r;
                 }
                 __syncthreads();
+                if (a.sigma_only) break;          // the colour branch does not feed the density
             }
             const int K = FN_H + (l == L.trunk_hidden ? L.kx_pad : 0);
             init_bias(reinterpret_cast<const float*>(pk + L.hid_b[l]), acc, tid);
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
             __syncthreads();
         }
         // ---- rgb head: sigmoid(Linear(256 -> 3)) ----
-        {
+        if (!a.sigma_only) {
             const float* rw = reinterpret_cast<const float*>(pk + L.rgb_w);
             for (int it = tid; it < TM * 3; it += NTHREADS) {
                 int pt = it % TM, o = it / TM;
@@ -309,13 +311,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
 
 int siren_points_exact(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs,
-                       const int32_t* only_idx, int n_only, float* out, cudaStream_t st) {
+                       const int32_t* only_idx, int n_only, float* out, cudaStream_t st, int sigma_only) {
     static_assert(sizeof(Smem<4>) <= 113 * 1024, "two CTAs per SM must fit");
     constexpr int TM = 64;
     ExactArgs a;
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.only_idx = only_idx; a.out = out;
     a.n_only_dev = nullptr;
     a.ppb = ppb; a.n_only = n_only; a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs;
+    a.sigma_only = sigma_only ? 1 : 0;
     a.tiles_per_batch = (ppb + TM - 1) / TM;
     const bool gather = only_idx != nullptr;
     a.n_items = gather ? ((long long)n_only + TM - 1) / TM : (long long)batch * a.tiles_per_batch;
@@ -372,6 +375,7 @@ int guard_refine(const FnLayout& L, const unsigned char* packed, const float* po
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = raw;
     a.only_idx = scratch_idx + 1; a.n_only_dev = scratch_idx; a.n_only = 0; a.n_items = 0;
     a.ppb = rays_per_batch * num_steps; a.tiles_per_batch = 1; a.dir_group = num_steps; a.lock_dirs = lock_dirs;
+    a.sigma_only = 1;      // only the sign of the far sample's density matters; its colour stays the tcgen05 one
     // 16-point tiles: the guard list is a few thousand points at most, so spread it over every SM and
     // keep each tile's latency low (one wave of 64-point tiles idles most of the chip for ~0.3 ms)
     size_t smem = sizeof(Smem<1>);
