@@ -137,3 +137,9 @@ def build_mirror(case, device="cpu"):
 def avg_film_draws(case):
     """The generate_avg_frequencies draws a staged_forward makes first (generators.py:142, 554)."""
     return [torch.randn(10000, 256) for _ in range(n_latents(case.model))]
+
+
+def loss_weights(shape):
+    """Fixed projection of rendered frames to a scalar for the gradient goldens: L = sum(pixels * W)."""
+    g = torch.Generator().manual_seed(99)
+    return torch.randn(shape, generator=g)

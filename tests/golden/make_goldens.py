@@ -75,5 +75,47 @@ def main():
             case.name, tuple(pixels.shape), float(pixels.abs().mean()), os.path.basename(path), os.path.getsize(path) / 1024))
 
 
+# ---- gradients of the differentiable call (the reference's G step / inversion path) -----------------
+GRAD_CASES = ("a_small", "d_small")
+#: parameters whose gradients are stored (a cross-section of trunk, heads, colour branch, mapping network)
+GRAD_PARAMS = {
+    "A": ["siren.network.0.layer.weight", "siren.network.7.layer.bias", "siren.final_layer.weight",
+          "siren.color_layer_sine.layer.bias", "siren.color_layer_linear.0.weight",
+          "siren.mapping_network.network.8.bias"],
+    "D": ["siren.network.0.layer.weight", "siren.network.7.layer.bias", "siren.final_layer.weight",
+          "siren.color_layer_sine.2.layer.bias", "siren.color_layer_linear.0.weight",
+          "siren.label_layer_linear.1.weight", "siren.geo_mapping_network.network.8.bias",
+          "siren.app_mapping_network.network.8.bias"],
+}
+
+
+def grad_goldens():
+    """tests/golden/grad_<case>.npz: d L / d (latents, selected parameters) of the reference's forward with
+    autograd on, same seed protocol (and therefore the same random draws) as the forward goldens."""
+    ref_generators, ref_siren, _ = ref_shim.load()
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for name in GRAD_CASES:
+        case = _cases.CASE_BY_NAME[name]
+        gen, _ = build_reference(case, ref_generators, ref_siren)
+        latents = tuple(z.clone().requires_grad_(True) for z in _cases.make_latents(case))
+        torch.manual_seed(case.seed)
+        pixels, _ = gen(*latents, **_cases.reference_kwargs(case))
+        loss = (pixels * _cases.loss_weights(pixels.shape)).sum()
+        loss.backward()
+        params = dict(gen.named_parameters())
+        out = {"loss": np.array(loss.item())}
+        for i, z in enumerate(latents):
+            out["latent%d" % i] = z.grad.numpy()
+        for k in GRAD_PARAMS[case.model]:
+            out[k] = params[k].grad.numpy()
+        path = os.path.join(out_dir, "grad_%s.npz" % name)
+        np.savez_compressed(path, **out)
+        print("%-28s loss %.6f  %d gradient tensors -> %s (%.1f KB)" % (
+            name, loss.item(), len(out) - 1, os.path.basename(path), os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:2] == ["--grads"]:
+        grad_goldens()
+    else:
+        main()

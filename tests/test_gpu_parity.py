@@ -244,6 +244,36 @@ def test_grad_requiring_call_fails_loudly_without_opt_in(monkeypatch):
         gen(torch.randn(1, 256, device=DEV), **case.cfg)
 
 
+@pytest.mark.parametrize("name", ["a_small", "d_small"])
+def test_opt_in_autograd_path_matches_reference_gradients(monkeypatch, name):
+    """FENERF_B200_TORCH_AUTOGRAD=1 (fenerf_b200/autograd_path.py: CUDA ray set-up / resampling, torch ops for
+    the differentiable stages) against the reference's own autograd: d sum(pixels * W) / d (latents, weights),
+    stored by tests/golden/make_goldens.py --grads."""
+    import os
+    monkeypatch.setenv("FENERF_B200_TORCH_AUTOGRAD", "1")
+    case = _cases.CASE_BY_NAME[name]
+    run = _harness.oracle_run(case)            # the reference's draws for this seed
+    gold = np.load(os.path.join(_cases.GOLDEN_DIR, "grad_%s.npz" % name))
+    gen = _cases.build_mirror(case, DEV)
+    latents = [_cuda(z).requires_grad_(True) for z in run["latents"]]
+    pixels, _ = gen(*latents, **dict(case.cfg, _rng=ReplayRng(run["draws"], DEV)))
+    assert (pixels.detach().cpu() - run["out"]["pixels"]).abs().max() <= 2e-4
+    loss = (pixels * _cases.loss_weights(pixels.shape).to(DEV)).sum()
+    assert abs(loss.item() - float(gold["loss"])) <= 2e-3 * max(1.0, abs(float(gold["loss"])))
+    loss.backward()
+    got = {"latent%d" % i: z.grad for i, z in enumerate(latents)}
+    got.update({k: p.grad for k, p in gen.named_parameters()})
+    for key in gold.files:
+        if key == "loss":
+            continue
+        want = torch.from_numpy(gold[key])
+        have = got[key].detach().cpu()
+        scale = want.abs().max().item()
+        assert scale > 0, key
+        assert (have - want).abs().max().item() <= 2e-3 * scale, "gradient of %s: max diff %g vs scale %g" % (
+            key, (have - want).abs().max().item(), scale)
+
+
 def test_repack_after_inplace_weight_update():
     case = _cases.CASE_BY_NAME["a_small"]
     gen = _cases.build_mirror(case, DEV)
