@@ -5,16 +5,23 @@
 // and the TMEM->register path each need ~2048 cycles, a layer is a dependency chain
 // MMA -> epilogue -> MMA, a ring slot's turnaround is ~1800 cycles whatever its size, and the MMA
 // issuer pays ~400 cycles of barrier/commit bookkeeping per ring round.  Hence:
-//   * TWO tiles per CTA (one CTA per SM) run the same layer program half a layer apart, so one
-//     tile's epilogue (MUFU + TMEM reads) overlaps the other tile's MMA phase;
+//   * TWO tiles per CTA (one CTA per SM) run the same layer program, each with its own MMA-issuer warp
+//     and its own four epilogue warps, so one tile's epilogue (MUFU + TMEM reads) and the ~1000 cycles
+//     an in-order issuer spends between two of its phases overlap the other tile's MMAs;
 //   * ring slots are 32 KB = two k-chunks of one feature half = 8 MMAs = 512 tensor cycles per
-//     barrier round; three slots (96 KB in flight) keep one 32 KB load arriving every ~600 cycles;
+//     barrier round; three slots (96 KB in flight), reused in global round-robin over both tiles' loads;
+//   * per layer the rounds run [h0 k01][h1 k01][h0 k23][h1 k23] and accumulator / operand hand-offs are
+//     per feature half: half 0 is committed after round 3 (its epilogue overlaps round 4) and the next
+//     layer's first round only needs half 0 of the previous epilogue;
 //   * that ring only fits because the per-tile 16 KB input chunk is gone: the position slots of the
 //     first layer live in activation chunk 3 (free at tile start), and the view-direction / grid
-//     feature slots of the first colour layer are written into activation chunk 0 AFTER that layer's
-//     main MMAs have retired (one extra barrier round trip per tile);
+//     feature slots of the first colour layer are written into activation chunk 0 once that layer's
+//     k01 rounds have retired (the k23 rounds cover the round trip);
 //   * activations are MN-major (points contiguous), so the feature-per-thread epilogue stores 16
-//     bytes at a time; TMEM is drained in 16-column double-buffered pieces.
+//     bytes at a time; TMEM is drained in 16-column double-buffered pieces;
+//   * the trunk head and the first colour layer of a tile are issued back to back (the other tile is in
+//     a long epilogue then), every stage kind has an unrolled issue path, and the next tile's point
+//     inputs are requested during the previous tile's last stage.
 //
 //   warps 0..2    weight producers (one per ring slot)
 //   warps 3, 4    MMA issuers of tile X / tile Y (warp-converged, elect.sync)
