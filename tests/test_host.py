@@ -131,23 +131,6 @@ def test_cpu_tensors_and_missing_library_fail_loudly(monkeypatch):
         _lib.lib()
 
 
-def test_install_aliases_reference_import_paths():
-    import fenerf_b200
-    saved = {k: sys.modules.get(k) for k in ("generators", "generators.generators", "siren", "siren.siren")}
-    try:
-        fenerf_b200.install()
-        import generators
-        import siren.siren as ss
-        assert getattr(generators, "DoubleImplicitGenerator3d").__module__ == "fenerf_b200.generators.generators"
-        assert hasattr(ss, "TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96") and hasattr(ss, "TALLSIREN")
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
-
-
 def test_module_pickles_without_device_buffers():
     import pickle
     gen = _cases.build_mirror(_cases.CASE_BY_NAME["a_small"])
