@@ -342,8 +342,7 @@ def field_roofline(gen, args, latents, md, device):
         rd = ops.make_render_desc(batch=B, img_size=R, num_steps=S, hierarchical=True, clamp_mode='relu', nerf_noise=0.0,
                                   fov=md["fov"], precision=args.precision)
         x_lin, y_lin, z_lin = vr.ray_tables(R, S, md["ray_start"], md["ray_end"], device)
-        origin, _, _ = vr.sample_camera_positions(device, n=B, horizontal_stddev=0.3, vertical_stddev=0.155, mode='gaussian')
-        c2w = vr.create_cam2world_matrix(vr.normalize_vecs(-origin), origin, device=device).contiguous()
+        c2w, _, _ = ops.camera_poses(B, 'gaussian', 0.3, 0.155, md["h_mean"], md["v_mean"], vr.DeviceRng(device), device)
         durations = []
         for it in range(6):
             pts, z, dirs, org = ops.ray_setup(rd, x_lin, y_lin, z_lin, c2w, torch.rand(B, N, S, 1, device=device))

@@ -18,12 +18,13 @@ FILL_MODE = {None: 0, "debug": 1, "weight": 2, "weight_debug": 3, "seg_padding_b
              "eval_seg_padding_background": 5, "eval_white_back": 6}
 FILL_COLOR = {"black": 0.0, "white": 1.0, "grey": 0.5, "light_grey": 0.81}
 E_CLAMP_MODE = -5
-CAMERA_MODE = {None: 0, "uniform": 1, "normal": 2, "gaussian": 2}
+CAMERA_MODE = {"uniform": 1, "normal": 2, "gaussian": 2, "truncated_gaussian": 3, "spherical_uniform": 4}
 
 EXPORTS = (
     "fenerf_packed_bytes", "fenerf_pack_field", "fenerf_siren_points", "fenerf_ray_setup", "fenerf_resample",
     "fenerf_composite", "fenerf_workspace_bytes", "fenerf_render_forward", "fenerf_last_error",
     "fenerf_abi_version", "fenerf_launch_count", "fenerf_debug_trace", "fenerf_camera_poses",
+    "fenerf_field_fingerprint",
 )
 
 
@@ -61,6 +62,8 @@ def _declare(lib):
     lib.fenerf_packed_bytes.argtypes = [P(FieldDesc)]
     lib.fenerf_pack_field.restype = C.c_int
     lib.fenerf_pack_field.argtypes = [P(FieldDesc), P(FieldParams), vp, sz, vp]
+    lib.fenerf_field_fingerprint.restype = C.c_int
+    lib.fenerf_field_fingerprint.argtypes = [P(FieldDesc), P(FieldParams), vp, vp]
     lib.fenerf_siren_points.restype = C.c_int
     lib.fenerf_siren_points.argtypes = [P(FieldDesc), vp, vp, vp, vp, i32, i64, i32, i32, vp, i32, vp, vp]
     lib.fenerf_camera_poses.restype = C.c_int

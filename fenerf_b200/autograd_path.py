@@ -81,10 +81,7 @@ def _render_autograd(gen, film, batch_size, img_size, fov, ray_start, ray_end, n
     n_rays = img_size * img_size
     with torch.no_grad():
         rng_perturb = rng.rand(batch_size, n_rays, num_steps, 1).contiguous()
-        origin, pitch, yaw = vr.sample_camera_positions(
-            n=batch_size, r=1, horizontal_stddev=h_stddev, vertical_stddev=v_stddev, horizontal_mean=h_mean,
-            vertical_mean=v_mean, device=device, mode=sample_dist, rng=rng)
-        cam2world = vr.create_cam2world_matrix(vr.normalize_vecs(-origin), origin, device=device).contiguous()
+        cam2world, pitch, yaw = ops.camera_poses(batch_size, sample_dist, h_stddev, v_stddev, h_mean, v_mean, rng, device)
         x_lin, y_lin, z_lin = vr.ray_tables(img_size, num_steps, ray_start, ray_end, device)
         rd = ops.make_render_desc(batch=batch_size, img_size=img_size, num_steps=num_steps,
                                   hierarchical=hierarchical_sample, clamp_mode=kwargs['clamp_mode'],

@@ -90,6 +90,15 @@ int fenerf_pack_field(const fenerf_field_desc* field, const fenerf_field_params*
     return pack_field(field, L, params, packed, (cudaStream_t)stream);
 }
 
+int fenerf_field_fingerprint(const fenerf_field_desc* field, const fenerf_field_params* params, uint64_t* out,
+                             void* stream) {
+    FnLayout L;
+    FN_REQUIRE(fn_make_layout(field, &L) == 0, "unsupported field description");
+    FN_REQUIRE(params && out, "params/out is NULL");
+    FN_REQUIRE(((uintptr_t)out & 7) == 0, "out must be 8-byte aligned");
+    return field_fingerprint(L, params, reinterpret_cast<unsigned long long*>(out), (cudaStream_t)stream);
+}
+
 int fenerf_siren_points(const fenerf_field_desc* field, const void* packed, const float* points, const float* dirs,
                         const float* film, int32_t batch, int64_t points_per_batch, int32_t dir_group,
                         int32_t precision, const int32_t* only_idx, int32_t n_only, float* out, void* stream) {
@@ -116,7 +125,7 @@ int fenerf_camera_poses(int32_t n, int32_t mode, float h_stddev, float v_stddev,
                         const float* draw_theta, const float* draw_phi, float* cam2world, float* pitch, float* yaw,
                         void* stream) {
     FN_REQUIRE(n >= 1 && cam2world && pitch && yaw, "bad argument");
-    FN_REQUIRE(mode >= FENERF_CAMERA_FIXED && mode <= FENERF_CAMERA_GAUSSIAN, "unsupported camera mode %d", mode);
+    FN_REQUIRE(mode >= FENERF_CAMERA_FIXED && mode <= FENERF_CAMERA_SPHERICAL_UNIFORM, "unsupported camera mode %d", mode);
     FN_REQUIRE(mode == FENERF_CAMERA_FIXED || (draw_theta && draw_phi), "camera mode %d needs the two random draws", mode);
     return camera_poses(n, mode, h_stddev, v_stddev, h_mean, v_mean, draw_theta, draw_phi, cam2world, pitch, yaw,
                         (cudaStream_t)stream);
@@ -194,8 +203,10 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
                           rd->precision, raw_c, st)) return e;
     if (rd->precision == FENERF_PRECISION_GUARD) {
         float tau = rd->guard_tau > 0.f ? rd->guard_tau : 1.5e-3f;
+        const int n_samples = rd->hierarchical ? 2 * rd->num_steps : rd->num_steps;
         if (int e = guard_refine(L, (const unsigned char*)packed, points_c, dirs, film, rd->batch, rays, rd->num_steps,
-                                 rd->lock_view_dependence, tau, raw_c, guard, st)) return e;
+                                 rd->lock_view_dependence, tau, noise_f ? noise_f + (n_samples - 1) : nullptr, n_samples,
+                                 rd->noise_std, raw_c, guard, st)) return e;
     }
     if (rd->hierarchical) {
         if (int e = resample(rd, C, raw_c, z_c, dirs, origins, noise_c, rng_u, z_f, points_f, (long long*)inds_dbg, st)) return e;

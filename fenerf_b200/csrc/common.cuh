@@ -46,15 +46,36 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
         if (!(cond)) return fn::fail(FENERF_E_ARG, __VA_ARGS__); \
     } while (0)
 
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
+// SM count of the CURRENT device (cached per device: one process may render on several GPUs)
 inline int num_sms() {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-        if (cached <= 0) cached = 148;
+    static std::atomic<int> cached[kMaxDevices];
+    const int dev = current_device();
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): remember the largest value set on each
+// device (`state` is one array per kernel instantiation) and raise it when a launch needs more.
+template <typename F>
+inline cudaError_t ensure_dynamic_smem(F kernel, std::atomic<int>* state /*[kMaxDevices]*/, int bytes) {
+    const int dev = current_device();
+    if (state[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) state[dev].store(bytes, std::memory_order_release);
+    return e;
 }
 
 // ---- entry points of the individual translation units (called by abi.cu) ----
@@ -63,6 +84,7 @@ int pack_field(const fenerf_field_desc* f, const FnLayout& L, const fenerf_field
 int siren_points_exact(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs,
                        const int32_t* only_idx, int n_only, float* out, cudaStream_t st, int sigma_only = 0);
+int field_fingerprint(const FnLayout& L, const fenerf_field_params* p, unsigned long long* out, cudaStream_t st);
 void set_fast_trace(long long* buf);
 long long* get_fast_trace();
 int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
@@ -70,6 +92,7 @@ int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const flo
                        long long* trace, int sigma_only, cudaStream_t st);
 int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                  const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
+                 const float* noise_far, long long noise_stride, float noise_std,
                  float* raw, int32_t* scratch_idx, cudaStream_t st);
 int camera_poses(int n, int mode, float h_std, float v_std, float h_mean, float v_mean, const float* draw_theta,
                  const float* draw_phi, float* c2w, float* pitch, float* yaw, cudaStream_t st);

@@ -266,11 +266,8 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
     A.n_pad = (A.n_samples + 3) & ~3;
     A.warp_floats = (4 * A.n_pad + A.n_samples * C + 3) & ~3;
     const size_t smem = (size_t)kRaysPerBlock * A.warp_floats * sizeof(float);
-    static size_t smem_allowed = 48 * 1024;
-    if (smem > smem_allowed) {
-        FN_CUDA_OK(cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_allowed = smem;
-    }
+    static std::atomic<int> smem_set[kMaxDevices];
+    if (smem > 48 * 1024) FN_CUDA_OK(ensure_dynamic_smem(composite_kernel, smem_set, (int)smem));
     long long groups = (A.n_rays + kRaysPerBlock - 1) / kRaysPerBlock;
     int per_sm = (int)(200 * 1024 / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);

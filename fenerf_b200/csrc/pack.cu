@@ -180,7 +180,65 @@ __global__ void pack_grid_kernel(const float* __restrict__ in, float* __restrict
     }
 }
 
+// ---- fingerprint of the raw parameters (EMA copy_to / restore write through .data without bumping
+// torch's version counter, so the host cannot see that the packed copy went stale) ------------------
+struct FpSegments {
+    const float* ptr[40];
+    unsigned long long count[40];
+    int n;
+};
+
+__global__ void fingerprint_kernel(FpSegments seg, unsigned long long* __restrict__ out) {
+    unsigned long long h0 = 0, h1 = 0;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long base = 0;
+    for (int s = 0; s < seg.n; ++s) {
+        const unsigned int* p = reinterpret_cast<const unsigned int*>(seg.ptr[s]);
+        for (unsigned long long i = tid; i < seg.count[s]; i += stride) {
+            const unsigned long long x = p[i], pos = base + i;
+            // position-weighted sums modulo 2^64 (commutative: atomics keep them deterministic)
+            h0 += (x + 0x9E3779B97F4A7C15ull) * (2 * pos + 1);
+            unsigned long long y = x * 0xBF58476D1CE4E5B9ull + pos;
+            y ^= y >> 29;
+            h1 += y * 0x94D049BB133111EBull;
+        }
+        base += seg.count[s];
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        h0 += __shfl_xor_sync(0xffffffffu, h0, off);
+        h1 += __shfl_xor_sync(0xffffffffu, h1, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, h0);
+        atomicAdd(out + 1, h1);
+    }
+}
+
 }  // namespace
+
+int field_fingerprint(const FnLayout& L, const fenerf_field_params* p, unsigned long long* out, cudaStream_t st) {
+    FpSegments seg;
+    seg.n = 0;
+    auto add = [&](const float* ptr, unsigned long long count) {
+        if (ptr && count) { seg.ptr[seg.n] = ptr; seg.count[seg.n] = count; ++seg.n; }
+    };
+    const int n_trunk = L.trunk_hidden + 1, n_color = L.n_hidden - L.trunk_hidden;
+    for (int i = 0; i < n_trunk; ++i) { add(p->trunk_w[i], (i == 0 ? 3 : FN_H) * FN_H); add(p->trunk_b[i], FN_H); }
+    add(p->sigma_w, FN_H); add(p->sigma_b, 1);
+    for (int i = 0; i < n_color; ++i) { add(p->color_w[i], (unsigned long long)(i == 0 ? L.kx + FN_H : FN_H) * FN_H); add(p->color_b[i], FN_H); }
+    add(p->rgb_w, 3 * FN_H); add(p->rgb_b, 3);
+    if (L.label_dim > 0) {
+        add(p->label_w[0], FN_H * FN_H); add(p->label_b[0], FN_H);
+        add(p->label_w[1], FN_H * FN_H); add(p->label_b[1], FN_H);
+        add(p->label_w[2], (unsigned long long)L.label_dim * FN_H); add(p->label_b[2], L.label_dim);
+    }
+    if (L.grid_channels > 0) add(p->grid, (unsigned long long)L.grid_channels * L.grid_res * L.grid_res * L.grid_res);
+    FN_CUDA_OK(cudaMemsetAsync(out, 0, 16, st));
+    fingerprint_kernel<<<num_sms() * 4, 256, 0, st>>>(seg, out);
+    FN_LAUNCH_OK("fingerprint_kernel");
+    return 0;
+}
 
 int pack_field(const fenerf_field_desc* f, const FnLayout& L, const fenerf_field_params* p, void* packed_v,
                cudaStream_t st) {

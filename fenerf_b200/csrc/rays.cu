@@ -75,7 +75,7 @@ ray_setup_kernel(int B, int H, int W, int S, float tan_half, const float* __rest
 
 // Camera pose -> 4x4 camera-to-world, one thread per image.  Same operation order as
 // sample_camera_positions + create_cam2world_matrix (volumetric_rendering.py:179-248) after the
-// random draws: theta = draw * stddev + mean (or the uniform / fixed variants), phi clamped to
+// random draws: theta = draw * stddev + mean (or the uniform / truncated / spherical / fixed variants), phi clamped to
 // [1e-5, pi - 1e-5], origin on the unit sphere, look-at with up = (0, 1, 0).
 __global__ void camera_kernel(int n, int mode, float h_std, float v_std, float h_mean, float v_mean,
                               const float* __restrict__ draw_theta, const float* __restrict__ draw_phi,
@@ -89,6 +89,19 @@ __global__ void camera_kernel(int n, int mode, float h_std, float v_std, float h
     } else if (mode == 2) {     // normal / gaussian: z * stddev + mean
         theta = __fadd_rn(__fmul_rn(draw_theta[b], h_std), h_mean);
         phi = __fadd_rn(__fmul_rn(draw_phi[b], v_std), v_mean);
+    } else if (mode == 3) {     // truncated_gaussian: of four normal draws the first inside (-2, 2), else the first
+        auto pick = [](const float* d) {
+            for (int i = 0; i < 4; ++i)
+                if (d[i] < 2.f && d[i] > -2.f) return d[i];
+            return d[0];
+        };
+        theta = __fadd_rn(__fmul_rn(pick(draw_theta + 4 * b), h_std), h_mean);
+        phi = __fadd_rn(__fmul_rn(pick(draw_phi + 4 * b), v_std), v_mean);
+    } else if (mode == 4) {     // spherical_uniform: theta uniform, phi = arccos(1 - 2 v), v uniform (v_std, v_mean pre-divided by pi)
+        theta = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(draw_theta[b], 0.5f), 2.f), h_std), h_mean);
+        float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(draw_phi[b], 0.5f), 2.f), v_std), v_mean);
+        v = fminf(fmaxf(v, 1e-5f), 1.f - 1e-5f);
+        phi = acosf(__fsub_rn(1.f, __fmul_rn(2.f, v)));
     } else {                    // fixed pose
         theta = h_mean;
         phi = v_mean;

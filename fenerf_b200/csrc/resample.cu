@@ -48,8 +48,7 @@ resample_kernel(long long n_rays, long long rays_per_batch, int S, int C, int cl
         const long long base = ray * S;
         for (int s = lane; s < S; s += 32) z[s] = z_vals[base + s];
         __syncwarp();
-        // the far sample (s = S-1) never enters the interior weights: it is not read, so the GUARD refinement
-        // of that sample may run concurrently (fenerf_render_forward)
+        // the far sample (s = S-1) never enters the interior weights, so it is not read
         for (int s = lane; s < S - 1; s += 32) {
             float sig = raw[(base + s) * C + (C - 1)];
             if (noise) sig = __fadd_rn(sig, __fmul_rn(noise[base + s], noise_std));

@@ -347,12 +347,16 @@ int siren_points_exact(const FnLayout& L, const unsigned char* packed, const flo
 // coarse mid-point).
 namespace {
 __global__ void guard_scan_kernel(const float* __restrict__ raw, long long n_rays, int S, int C, float tau,
+                                  const float* __restrict__ noise_far, long long noise_stride, float noise_std,
                                   int32_t* __restrict__ count, int32_t* __restrict__ list) {
     for (long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x; ray < n_rays;
          ray += (long long)gridDim.x * blockDim.x) {
         long long pt = ray * S + (S - 1);
         float sig = raw[pt * C + (C - 1)];
-        if (fabsf(sig) < tau || !isfinite(sig)) {
+        // the step of the final compositing sits at sigma + noise * noise_std = 0 (volumetric_rendering.py:27-32);
+        // the far sample is the last one after the merge, so its noise is draw #6 at [ray, n_samples - 1]
+        float pre = noise_far ? __fadd_rn(sig, __fmul_rn(noise_far[ray * noise_stride], noise_std)) : sig;
+        if (fabsf(pre) < tau || !isfinite(sig)) {
             int slot = atomicAdd(count, 1);
             list[slot] = (int32_t)pt;
         }
@@ -362,6 +366,7 @@ __global__ void guard_scan_kernel(const float* __restrict__ raw, long long n_ray
 
 int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                  const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
+                 const float* noise_far, long long noise_stride, float noise_std,
                  float* raw, int32_t* scratch_idx, cudaStream_t st) {
     long long n_rays = rays_per_batch * batch;
     FN_REQUIRE(n_rays * num_steps < 2147483647LL, "too many points for the 32-bit guard list");
@@ -369,7 +374,8 @@ int guard_refine(const FnLayout& L, const unsigned char* packed, const float* po
     int threads = 256;
     long long want = (n_rays + threads - 1) / threads;
     int blocks = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
-    guard_scan_kernel<<<blocks, threads, 0, st>>>(raw, n_rays, num_steps, L.out_dim, tau, scratch_idx, scratch_idx + 1);
+    guard_scan_kernel<<<blocks, threads, 0, st>>>(raw, n_rays, num_steps, L.out_dim, tau, noise_far, noise_stride, noise_std,
+                                                  scratch_idx, scratch_idx + 1);
     FN_LAUNCH_OK("guard_scan_kernel");
     ExactArgs a;
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = raw;

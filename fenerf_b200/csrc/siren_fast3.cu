@@ -643,19 +643,19 @@ int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const flo
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out;
     a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
     a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs; a.trace = trace;
-    {
-        const char* e = getenv("FENERF_B200_DEBUG_SHORT_LOADS");   // profiling aid, see tools/diag_fast.py
+#ifdef FENERF_DEBUG_SHORT_LOADS
+    {   // profiling aid (tools/diag_fast.py), wrong results by design: only in builds that define the macro
+        const char* e = getenv("FENERF_B200_DEBUG_SHORT_LOADS");
         a.debug_short_loads = (e && atoi(e)) ? 1 : 0;
+        if (a.debug_short_loads) fprintf(stderr, "fenerf_b200: FENERF_B200_DEBUG_SHORT_LOADS set -- RESULTS ARE WRONG (timing experiment)\n");
     }
+#endif
     if (a.n_tiles <= 0) return 0;
     FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);
     const long long n_pairs = (a.n_tiles + 1) / 2;
     auto kernel = a.trace ? siren_fast3_kernel<true> : siren_fast3_kernel<false>;
-    static bool attr_set[2] = {false, false};              // once per kernel instantiation
-    if (!attr_set[a.trace ? 1 : 0]) {
-        FN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-        attr_set[a.trace ? 1 : 0] = true;
-    }
+    static std::atomic<int> attr_set[2][kMaxDevices];      // per kernel instantiation and device
+    FN_CUDA_OK(ensure_dynamic_smem(kernel, attr_set[a.trace ? 1 : 0], (int)SMEM_TOTAL));
     int blocks = (int)(n_pairs < (long long)num_sms() ? n_pairs : (long long)num_sms());
     kernel<<<blocks, NTHREADS, SMEM_TOTAL, st>>>(a);
     FN_LAUNCH_OK("siren_fast3_kernel");

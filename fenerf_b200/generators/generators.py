@@ -30,20 +30,17 @@ class _RenderSkeleton:
         if device.type != 'cuda':
             raise RuntimeError("fenerf_b200 renders on CUDA only; move the generator to a B200 (got %s)" % device)
         rng = kwargs.get('_rng') or vr.DeviceRng(device)
+        if staged:
+            # EMA copy_to / restore write through .data: fingerprint-check the packed weights (host sync; the
+            # staged methods end in .cpu() anyway)
+            self.siren.packed(verify=True)
         n_rays = img_size * img_size
         n_samples = num_steps * 2 if hierarchical_sample else num_steps
         with torch.no_grad():
             # draw #1, then the camera draws (transform_sampled_points, volumetric_rendering.py:147-153)
             rng_perturb = rng.rand(batch_size, n_rays, num_steps, 1)
-            fused = ops.camera_poses(batch_size, sample_dist, h_stddev, v_stddev, h_mean, v_mean, rng, device)
-            if fused is not None:
-                cam2world, pitch, yaw = fused
-            else:   # rare camera modes: the torch helpers (same draw order)
-                camera_origin, pitch, yaw = vr.sample_camera_positions(
-                    n=batch_size, r=1, horizontal_stddev=h_stddev, vertical_stddev=v_stddev, horizontal_mean=h_mean,
-                    vertical_mean=v_mean, device=device, mode=sample_dist, rng=rng)
-                forward_vector = vr.normalize_vecs(-camera_origin)
-                cam2world = vr.create_cam2world_matrix(forward_vector, camera_origin, device=device).contiguous()
+            cam2world, pitch, yaw = ops.camera_poses(batch_size, sample_dist, h_stddev, v_stddev, h_mean, v_mean, rng,
+                                                     device)
             x_lin, y_lin, z_lin = ops.ray_tables(img_size, num_steps, ray_start, ray_end, device)
             rng_noise_c = rng_u = None
             if hierarchical_sample:

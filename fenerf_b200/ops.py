@@ -151,23 +151,33 @@ def needs_grad(module, *tensors):
 # render stages (exposed for stage-level parity tests and for callers that bring their own rays)
 # --------------------------------------------------------------------------------------------
 def camera_poses(n, mode, h_stddev, v_stddev, h_mean, v_mean, rng, device):
-    """Fused camera pose sampling + look-at matrix (one launch instead of ~45 tiny torch kernels).
-    Draw order as the reference: theta then phi.  Returns (cam2world (n,4,4), pitch (n,1), yaw (n,1)),
-    or None when `mode` is one the fused kernel does not cover (caller falls back to the torch helpers)."""
-    if mode not in _lib.CAMERA_MODE and mode in ("hybrid", "truncated_gaussian", "spherical_uniform"):
-        return None
+    """Camera pose sampling + look-at matrix in one launch (sample_camera_positions + create_cam2world_matrix,
+    generators/volumetric_rendering.py:170-248).  The draws are made here with `rng` in the reference's order
+    (theta then phi; 'hybrid' first flips Python's `random.random()`); every mode the reference names is
+    covered, anything else means "the mean pose" as in the reference's else-branch.
+    Returns (cam2world (n,4,4), pitch (n,1), yaw (n,1))."""
     code = _lib.CAMERA_MODE.get(mode, 0)
+    h_stddev, v_stddev, h_mean, v_mean = float(h_stddev), float(v_stddev), float(h_mean), float(v_mean)
+    if mode == "hybrid":
+        if rng.coin() < 0.5:
+            code, h_stddev, v_stddev = 1, 2 * h_stddev, 2 * v_stddev
+        else:
+            code = 2
     d_theta = d_phi = None
-    if code == 1:
+    if code in (1, 4):
         d_theta, d_phi = rng.rand(n, 1), rng.rand(n, 1)
     elif code == 2:
         d_theta, d_phi = rng.randn(n, 1), rng.randn(n, 1)
+    elif code == 3:
+        d_theta, d_phi = rng.randn(n, 1, 4), rng.randn(n, 1, 4)
+    if code == 4:
+        v_stddev, v_mean = v_stddev / math.pi, v_mean / math.pi
     c2w = torch.empty((n, 4, 4), dtype=torch.float32, device=device)
     pitch = torch.empty((n, 1), dtype=torch.float32, device=device)
     yaw = torch.empty((n, 1), dtype=torch.float32, device=device)
     with torch.cuda.device(device):
         _lib.check(_lib.lib().fenerf_camera_poses(
-            n, code, float(h_stddev), float(v_stddev), float(h_mean), float(v_mean),
+            n, code, h_stddev, v_stddev, h_mean, v_mean,
             _chk(d_theta.contiguous(), "draw_theta", device) if d_theta is not None else 0,
             _chk(d_phi.contiguous(), "draw_phi", device) if d_phi is not None else 0,
             c2w.data_ptr(), pitch.data_ptr(), yaw.data_ptr(), _stream(device)))

@@ -18,6 +18,15 @@ class PackedField:
     ptr: int                  # 1024-byte aligned device pointer inside `buffer`
     nbytes: int
     device: torch.device
+    stream: int = 0               # cuda stream the pack kernels ran on
+    event: "torch.cuda.Event" = None   # recorded after them: consumers on another stream wait on it
+    fingerprint: tuple = None     # (u64, u64) of the raw parameters at pack time, filled lazily
+
+    def wait_ready(self):
+        """Orders the caller's current stream after the pack kernels when it is a different stream."""
+        cur = torch.cuda.current_stream(self.device)
+        if self.event is not None and cur.cuda_stream != self.stream:
+            cur.wait_event(self.event)
 
 
 def field_desc(spec) -> "_lib.FieldDesc":
@@ -90,5 +99,25 @@ def pack_field(module) -> PackedField:
         params, keep = collect_params(module, device)
         stream = torch.cuda.current_stream(device).cuda_stream
         _lib.check(lib.fenerf_pack_field(C.byref(desc), C.byref(params), ptr, nbytes, stream))
+        event = torch.cuda.Event()
+        event.record()
         del keep
-    return PackedField(desc=desc, buffer=buf, ptr=ptr, nbytes=nbytes, device=device)
+    return PackedField(desc=desc, buffer=buf, ptr=ptr, nbytes=nbytes, device=device, stream=stream, event=event)
+
+
+def fingerprint(module):
+    """(u64, u64) fingerprint of the field's raw parameters -- one kernel + a 16-byte read-back, i.e. a
+    host synchronisation: used where the caller synchronises anyway (staged_forward*, whose outputs go to
+    the CPU) to catch parameter writes that bypass torch's version counters (torch_ema ``copy_to`` /
+    ``restore`` use ``param.data.copy_``)."""
+    lib = _lib.lib()
+    device = next(module.parameters()).device
+    desc = field_desc(module.field_spec())
+    with torch.cuda.device(device):
+        out = torch.empty(2, dtype=torch.int64, device=device)
+        params, keep = collect_params(module, device)
+        _lib.check(lib.fenerf_field_fingerprint(C.byref(desc), C.byref(params), out.data_ptr(),
+                                                torch.cuda.current_stream(device).cuda_stream))
+        a, b = out.tolist()
+        del keep
+    return a, b

@@ -164,22 +164,53 @@ class _FieldBase(nn.Module):
         raise NotImplementedError
 
     # -- packed-weight cache -------------------------------------------------------------
-    def _weights_version(self):
-        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+    def _field_parameters(self):
+        """The parameters the kernels consume (everything but the mapping networks, which stay in PyTorch)."""
+        plist = self.__dict__.get('_field_plist')
+        if plist is None or plist[0] != len(self._parameters) + sum(1 for _ in self.children()):
+            ps = [p for n, p in self.named_parameters() if 'mapping_network' not in n]
+            plist = (len(self._parameters) + sum(1 for _ in self.children()), ps)
+            self.__dict__['_field_plist'] = plist
+        return plist[1]
 
-    def packed(self):
-        """Kernel-layout weights, repacked when any parameter changed in place (optimizer / EMA)."""
+    def _weights_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self._field_parameters())
+
+    def packed(self, verify=False):
+        """Kernel-layout weights.  Repacked when a parameter's (storage, version) changed -- what optimizer
+        steps and in-place torch ops bump.  Writes through ``param.data`` (torch_ema ``copy_to`` / ``restore``,
+        train_double_latent_semantic.py:464-522) bump nothing: ``verify=True`` compares a device-side
+        fingerprint of the raw parameters with the one taken at pack time (one kernel + a 16-byte read-back,
+        so a host sync) -- the generators pass it from ``staged_forward*``, the methods the reference renders
+        EMA weights through, whose outputs go to the CPU anyway.  :meth:`invalidate_packed` forces a repack.
+        """
         from .. import packing
         ver = self._weights_version()
         cache = self.__dict__.get('_packed_cache')
+        if cache is not None and cache[0] == ver and verify:
+            fp = packing.fingerprint(self)
+            if cache[1].fingerprint is None:
+                # first verified use of this pack: nothing to compare with yet; a pack made by this very call
+                # chain is fresh, one made by an earlier non-verified call may already be stale -> repack once
+                cache = None
+            elif cache[1].fingerprint != fp:
+                cache = None
         if cache is None or cache[0] != ver:
             cache = (ver, packing.pack_field(self))
+            if verify:
+                cache[1].fingerprint = packing.fingerprint(self)
             self.__dict__['_packed_cache'] = cache
+        cache[1].wait_ready()
         return cache[1]
+
+    def invalidate_packed(self):
+        """Drop the kernel-layout copy of the weights (next render repacks)."""
+        self.__dict__.pop('_packed_cache', None)
 
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop('_packed_cache', None)  # never pickle device buffers derived from the weights
+        state.pop('_field_plist', None)
         return state
 
     # -- the point-network entry the reference's callers use --------------------------------

@@ -95,6 +95,14 @@ size_t fenerf_packed_bytes(const fenerf_field_desc* field);
 int fenerf_pack_field(const fenerf_field_desc* field, const fenerf_field_params* params,
                       void* packed, size_t packed_bytes, void* stream);
 
+/* 128-bit fingerprint of the raw parameters (two position-weighted sums modulo 2^64 over their bit
+ * patterns), written to `out[0..1]` on the device.  The host mirror compares it with the fingerprint taken
+ * at pack time to decide whether the packed copy is stale: torch_ema's copy_to / restore
+ * (render_multiview_images_double_semantic.py:63, train_double_latent_semantic.py:464-522) write through
+ * `param.data.copy_`, which torch's version counters do not see. */
+int fenerf_field_fingerprint(const fenerf_field_desc* field, const fenerf_field_params* params,
+                             uint64_t* out /* device, 2 x u64 */, void* stream);
+
 /* precision modes of the point network */
 #define FENERF_PRECISION_EXACT 0  /* fp32 FFMA + precise sinf everywhere (CUDA cores)            */
 #define FENERF_PRECISION_FAST  1  /* fp16 operands / fp32 accumulate on tcgen05, sin.approx      */
@@ -158,14 +166,21 @@ typedef struct fenerf_render_desc {
 
 /* Camera pose sampling after the random draws, and the look-at camera-to-world matrix.
  * Replaces the arithmetic of sample_camera_positions + create_cam2world_matrix
- * (generators/volumetric_rendering.py:179-248) for the modes the named curricula use; the caller
- * makes the draws (torch.rand / torch.randn (n,1), theta first) so the RNG stream is the reference's.
+ * (generators/volumetric_rendering.py:170-248); the caller makes the draws (theta first) so the RNG
+ * stream is the reference's.
  *   mode FIXED: theta = h_mean, phi = v_mean (draws may be NULL)
- *   mode UNIFORM: (draw - 0.5) * 2 * stddev + mean;  mode GAUSSIAN: draw * stddev + mean
+ *   mode UNIFORM: (draw - 0.5) * 2 * stddev + mean            draws torch.rand (n,1)
+ *   mode GAUSSIAN ('normal' / 'gaussian'): draw * stddev + mean   draws torch.randn (n,1)
+ *   mode TRUNCATED_GAUSSIAN: draws torch.randn (n,1,4); the first of the four inside (-2, 2) (:170-177)
+ *   mode SPHERICAL_UNIFORM: theta as UNIFORM; v = (draw - 0.5) * 2 * v_stddev + v_mean with v_stddev, v_mean
+ *        ALREADY divided by pi by the caller (:214), clamped to [1e-5, 1 - 1e-5]; phi = arccos(1 - 2 v)
+ *   'hybrid' (:198-204) is UNIFORM with doubled stddevs or GAUSSIAN, chosen by the caller's coin flip
  * out: cam2world (n,16) row-major; pitch (n) = clamped phi; yaw (n) = theta                        */
 #define FENERF_CAMERA_FIXED 0
 #define FENERF_CAMERA_UNIFORM 1
 #define FENERF_CAMERA_GAUSSIAN 2
+#define FENERF_CAMERA_TRUNCATED_GAUSSIAN 3
+#define FENERF_CAMERA_SPHERICAL_UNIFORM 4
 int fenerf_camera_poses(int32_t n, int32_t mode, float h_stddev, float v_stddev, float h_mean, float v_mean,
                         const float* draw_theta, const float* draw_phi, float* cam2world, float* pitch, float* yaw,
                         void* stream);

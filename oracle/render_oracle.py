@@ -45,6 +45,13 @@ class Draws:
         self.log.append(("randn", t))
         return t
 
+    def coin(self):
+        """Python's global `random.random()` ('hybrid' camera mode, volumetric_rendering.py:199)."""
+        import random
+        v = random.random()
+        self.log.append(("coin", torch.tensor(v, dtype=torch.float64)))
+        return v
+
 
 # --------------------------------------------------------------------------------------------
 # camera + rays        generators/volumetric_rendering.py:109-248
@@ -73,17 +80,38 @@ def jitter(points, z_vals, dirs, draws):
     return points + offset * dirs.unsqueeze(2), z_vals + offset
 
 
+def _first_inside_pm2(draws, n):
+    """truncated_normal_ (:170-177) with mean 0 / std 1: of four normal draws per entry, the first one inside
+    (-2, 2) (the first of the four if none is)."""
+    tmp = draws.randn(n, 1, 4)
+    valid = (tmp < 2) & (tmp > -2)
+    ind = valid.max(-1, keepdim=True)[1]
+    return tmp.gather(-1, ind).squeeze(-1) * 1 + 0
+
+
 def camera_pose(n, h_stddev, v_stddev, h_mean, v_mean, mode, draws):
-    """theta (yaw), phi (pitch) and the unit-sphere origin (sample_camera_positions, :179-228).
-    Only the modes the named curricula use are restated: gaussian/normal, uniform, and 'mean'."""
+    """theta (yaw), phi (pitch) and the unit-sphere origin (sample_camera_positions, :179-228)."""
     if mode == 'uniform':
         theta = (draws.rand(n, 1) - 0.5) * 2 * h_stddev + h_mean
         phi = (draws.rand(n, 1) - 0.5) * 2 * v_stddev + v_mean
     elif mode in ('normal', 'gaussian'):
         theta = draws.randn(n, 1) * h_stddev + h_mean
         phi = draws.randn(n, 1) * v_stddev + v_mean
-    elif mode in ('hybrid', 'truncated_gaussian', 'spherical_uniform'):
-        raise NotImplementedError("oracle: camera mode %r not restated" % mode)
+    elif mode == 'hybrid':
+        if draws.coin() < 0.5:
+            theta = (draws.rand(n, 1) - 0.5) * 2 * h_stddev * 2 + h_mean
+            phi = (draws.rand(n, 1) - 0.5) * 2 * v_stddev * 2 + v_mean
+        else:
+            theta = draws.randn(n, 1) * h_stddev + h_mean
+            phi = draws.randn(n, 1) * v_stddev + v_mean
+    elif mode == 'truncated_gaussian':
+        theta = _first_inside_pm2(draws, n) * h_stddev + h_mean
+        phi = _first_inside_pm2(draws, n) * v_stddev + v_mean
+    elif mode == 'spherical_uniform':
+        theta = (draws.rand(n, 1) - .5) * 2 * h_stddev + h_mean
+        v_std, v_mu = v_stddev / math.pi, v_mean / math.pi
+        v = torch.clamp((draws.rand(n, 1) - .5) * 2 * v_std + v_mu, 1e-5, 1 - 1e-5)
+        phi = torch.arccos(1 - 2 * v)
     else:
         theta = torch.ones((n, 1), dtype=torch.float) * h_mean
         phi = torch.ones((n, 1), dtype=torch.float) * v_mean

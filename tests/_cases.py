@@ -23,6 +23,9 @@ MODELS = {
     "B": ("DoubleImplicitGenerator3d", "TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96", 2, 22),
     "C": ("ImplicitGenerator3d", "SPATIALSIRENBASELINE", 1, 4),
     "D": ("DoubleImplicitGenerator3d", "SIRENBASELINESEMANTICDISENTANGLE", 2, 22),
+    # D with 19 label channels: the only width at which the reference's 'debug' / 'weight_debug' fill modes run at
+    # all -- they assign a hard-coded 22-vector to the (C-1)-channel pixels (volumetric_rendering.py:54, 66)
+    "E": ("DoubleImplicitGenerator3d", "SIRENBASELINESEMANTICDISENTANGLE", 2, 23),
 }
 
 
@@ -80,7 +83,41 @@ CASES = [
     Case("d_small", "D", 1, 32, _cfg(img_size=16, num_steps=12, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
     Case("d_staged_softmax", "D", 1, 33, _cfg(img_size=12, num_steps=10, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
                                               softmax_label=True, fill_mode='weight'), method="staged_forward", psi=0.7),
+    # ---- round 2: the branches round 1 left untested (VERDICT r1 "What's weak" 3) ----
+    # fill modes of fancy_integration (volumetric_rendering.py:53-102).  A random-init field has sigma ~ +-0.03, so
+    # weights_sum is ~1 where the far sample's sigma is positive (its interval is 1e10 wide) and ~0.01 elsewhere:
+    # both sides of the `weights_sum < 0.9` test occur in every image
+    Case("e_staged_debug", "E", 1, 41, _cfg(img_size=12, num_steps=10, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                            fill_mode='debug'), method="staged_forward", psi=0.7),
+    Case("e_staged_weight_debug", "E", 2, 42, _cfg(img_size=12, num_steps=10, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                                   fill_mode='weight_debug'), method="staged_forward", psi=0.7),
+    Case("b_staged_evalsegpad_white", "B", 1, 43, _cfg(img_size=12, num_steps=10, h_stddev=0.0, v_stddev=0.0,
+                                                       nerf_noise=0.0, fill_mode='eval_seg_padding_background',
+                                                       fill_color='white'), method="staged_forward", psi=0.7),
+    Case("d_staged_segpad_lightgrey", "D", 1, 44, _cfg(img_size=12, num_steps=10, h_stddev=0.0, v_stddev=0.0,
+                                                       nerf_noise=0.0, fill_mode='seg_padding_background',
+                                                       fill_color='light_grey'), method="staged_forward", psi=0.7),
+    Case("a_hier_softplus", "A", 1, 45, _cfg(img_size=16, num_steps=12, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                             clamp_mode='softplus')),
+    Case("b_noise_b2", "B", 2, 46, _cfg(img_size=12, num_steps=10, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.3)),
+    Case("d_b2", "D", 2, 47, _cfg(img_size=12, num_steps=10, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    # the three rare sample_dist modes (volumetric_rendering.py:198-219)
+    Case("a_cam_hybrid", "A", 2, 48, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0,
+                                          sample_dist='hybrid')),
+    Case("a_cam_hybrid2", "A", 2, 51, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0,
+                                           sample_dist='hybrid')),
+    Case("a_cam_truncgauss", "A", 3, 49, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0,
+                                              sample_dist='truncated_gaussian')),
+    Case("a_cam_spherical", "A", 2, 50, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0,
+                                             sample_dist='spherical_uniform')),
+    # ---- the benchmarked shapes themselves (BASELINE.json configs[1] and the configs[4] shape), one face each ----
+    Case("a_cfg2", "A", 1, 61, _cfg(img_size=128, num_steps=24, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("b_cfg2", "B", 1, 62, _cfg(img_size=128, num_steps=24, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("a_cfg5", "A", 1, 63, _cfg(img_size=256, num_steps=48, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
 ]
+#: cases whose CPU oracle run takes tens of seconds: the CPU suite (-m "not gpu") checks them only with
+#: FENERF_SLOW_TESTS=1; the GPU suite always runs them
+BIG_CASES = ("b_cfg2", "a_cfg5")
 CASE_BY_NAME = {c.name: c for c in CASES}
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

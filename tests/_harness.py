@@ -1,5 +1,6 @@
 """Runs the oracle for a parity case (CPU) -- shared by the CPU and the GPU tests."""
 import hashlib
+import random
 
 import torch
 
@@ -20,6 +21,7 @@ def oracle_run(case, gen=None, keep_stages=True):
     gen = gen or _cases.build_mirror(case, "cpu")
     latents = _cases.make_latents(case)
     torch.manual_seed(case.seed)
+    random.seed(case.seed)          # 'hybrid' camera mode flips Python's global coin (volumetric_rendering.py:199)
     avg_draws = None
     with torch.no_grad():
         film = oracle.film_from_latents(gen.siren, latents)

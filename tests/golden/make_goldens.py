@@ -11,10 +11,12 @@ Seed protocol (shared with tests/_cases.py):
   generator.set_device('cpu')     -> consumes the generate_avg_frequencies draws
   [case-specific weight edits, e.g. final_layer.bias += 0.5]
   torch.manual_seed(1000 + i)     -> latent i = randn(1, 256)    (geo, then app for model B)
-  torch.manual_seed(case.seed)    -> the forward under test
+  torch.manual_seed(case.seed)    -> the forward under test  (+ random.seed(case.seed): the 'hybrid' camera
+                                     mode flips Python's global coin, volumetric_rendering.py:199)
 """
 import hashlib
 import os
+import random
 import sys
 
 import numpy as np
@@ -57,6 +59,7 @@ def main():
         latents = _cases.make_latents(case)
         kw = _cases.reference_kwargs(case)
         torch.manual_seed(case.seed)
+        random.seed(case.seed)
         with torch.no_grad():
             if case.method == "forward":
                 pixels, poses = gen(*latents, **kw)

@@ -104,20 +104,6 @@ def test_replay_rng_enforces_kind_shape_and_order():
         r.randn(1)
 
 
-def test_camera_helpers_match_oracle():
-    from fenerf_b200.generators import volumetric_rendering as vr
-    d = oracle.Draws()
-    torch.manual_seed(3)
-    o1, phi1, th1 = oracle.camera_pose(5, 0.3, 0.155, 1.5, 1.6, 'gaussian', d)
-    torch.manual_seed(3)
-    o2, phi2, th2 = vr.sample_camera_positions('cpu', n=5, horizontal_stddev=0.3, vertical_stddev=0.155,
-                                               horizontal_mean=1.5, vertical_mean=1.6, mode='gaussian')
-    assert torch.equal(o1, o2) and torch.equal(phi1, phi2) and torch.equal(th1, th2)
-    m1 = oracle.look_at(oracle.unit(-o1), o1)
-    m2 = vr.create_cam2world_matrix(vr.normalize_vecs(-o2), o2, device='cpu')
-    assert torch.equal(m1, m2)
-
-
 def test_cpu_tensors_and_missing_library_fail_loudly(monkeypatch):
     case = _cases.CASE_BY_NAME["a_small"]
     gen = _cases.build_mirror(case)
