@@ -24,7 +24,9 @@ EXPORTS = (
     "fenerf_packed_bytes", "fenerf_pack_field", "fenerf_siren_points", "fenerf_ray_setup", "fenerf_resample",
     "fenerf_composite", "fenerf_workspace_bytes", "fenerf_render_forward", "fenerf_last_error",
     "fenerf_abi_version", "fenerf_launch_count", "fenerf_debug_trace", "fenerf_camera_poses",
-    "fenerf_field_fingerprint",
+    "fenerf_field_fingerprint", "fenerf_composite_backward", "fenerf_film_forward_stash", "fenerf_gate_backward",
+    "fenerf_head_grads", "fenerf_extras_gather", "fenerf_grid_scatter_add", "fenerf_grid_unpack_grad",
+    "fenerf_workspace_layout",
 )
 
 
@@ -52,6 +54,11 @@ class RenderDesc(C.Structure):
                 ("noise_std", C.c_float), ("tan_half_fov", C.c_float), ("guard_tau", C.c_float)]
 
 
+class WorkspaceOffsets(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("points_coarse", "z_coarse", "dirs", "origins", "raw_coarse", "z_fine",
+                                          "points_fine", "raw_fine", "total")]
+
+
 _lib = None
 
 
@@ -76,8 +83,24 @@ def _declare(lib):
     lib.fenerf_composite.argtypes = [P(RenderDesc), i32] + [vp] * 11
     lib.fenerf_workspace_bytes.restype = sz
     lib.fenerf_workspace_bytes.argtypes = [P(RenderDesc), P(FieldDesc)]
+    lib.fenerf_workspace_layout.restype = C.c_int
+    lib.fenerf_workspace_layout.argtypes = [P(RenderDesc), P(FieldDesc), P(WorkspaceOffsets)]
     lib.fenerf_render_forward.restype = C.c_int
     lib.fenerf_render_forward.argtypes = [P(RenderDesc), P(FieldDesc)] + [vp] * 15 + [vp, sz, vp]
+    lib.fenerf_composite_backward.restype = C.c_int
+    lib.fenerf_composite_backward.argtypes = [P(RenderDesc), i32] + [vp] * 9
+    lib.fenerf_film_forward_stash.restype = C.c_int
+    lib.fenerf_film_forward_stash.argtypes = [vp, vp, vp, i64, i64, i64, vp, i32, vp, vp, vp, i32, vp]
+    lib.fenerf_gate_backward.restype = C.c_int
+    lib.fenerf_gate_backward.argtypes = [vp, vp, i64, i64, vp, i32, vp]
+    lib.fenerf_head_grads.restype = C.c_int
+    lib.fenerf_head_grads.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, i32, vp]
+    lib.fenerf_extras_gather.restype = C.c_int
+    lib.fenerf_extras_gather.argtypes = [P(FieldDesc), vp, vp, vp, i64, i64, i32, i32, vp, vp]
+    lib.fenerf_grid_scatter_add.restype = C.c_int
+    lib.fenerf_grid_scatter_add.argtypes = [P(FieldDesc), vp, vp, i32, i64, vp, i32, vp]
+    lib.fenerf_grid_unpack_grad.restype = C.c_int
+    lib.fenerf_grid_unpack_grad.argtypes = [P(FieldDesc), vp, vp, vp, vp]
     lib.fenerf_last_error.restype = C.c_char_p
     lib.fenerf_last_error.argtypes = []
     lib.fenerf_abi_version.restype = i32

@@ -165,6 +165,16 @@ size_t fenerf_workspace_bytes(const fenerf_render_desc* rd, const fenerf_field_d
     return plan_workspace(rd, field->out_dim).total;
 }
 
+int fenerf_workspace_layout(const fenerf_render_desc* rd, const fenerf_field_desc* field, fenerf_workspace_offsets* out) {
+    if (int e = check_render_desc(rd)) return e;
+    FN_REQUIRE(field && out, "NULL argument");
+    Workspace w = plan_workspace(rd, field->out_dim);
+    out->points_coarse = w.points_c; out->z_coarse = w.z_c; out->dirs = w.dirs; out->origins = w.origins;
+    out->raw_coarse = w.raw_c; out->z_fine = w.z_f; out->points_fine = w.points_f; out->raw_fine = w.raw_f;
+    out->total = w.total;
+    return 0;
+}
+
 int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc* field, const void* packed,
                           const float* film, const float* x_lin, const float* y_lin, const float* z_lin,
                           const float* cam2world, const float* rng_perturb, const float* rng_noise_c,
@@ -215,6 +225,68 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
     }
     return composite(rd, C, raw_c, z_c, rd->hierarchical ? raw_f : nullptr, rd->hierarchical ? z_f : nullptr, noise_f,
                      pixels, depth, weights_sum, weights, nullptr, st);
+}
+
+// ---- backward ---------------------------------------------------------------
+int fenerf_composite_backward(const fenerf_render_desc* rd, int32_t out_dim, const float* raw_coarse, const float* z_coarse,
+                              const float* raw_fine, const float* z_fine, const float* rng_noise, const float* d_pixels,
+                              float* d_raw_coarse, float* d_raw_fine, void* stream) {
+    if (int e = check_render_desc(rd)) return e;
+    FN_REQUIRE(raw_coarse && z_coarse && d_pixels && d_raw_coarse, "NULL argument");
+    FN_REQUIRE(rd->noise_std == 0.f || rng_noise, "noise_std != 0 needs rng_noise");
+    return composite_backward(rd, out_dim, raw_coarse, z_coarse, raw_fine, z_fine, rd->noise_std != 0.f ? rng_noise : nullptr,
+                              d_pixels, d_raw_coarse, d_raw_fine, (cudaStream_t)stream);
+}
+
+int fenerf_film_forward_stash(const float* z, const float* bias, const float* film_layer, int64_t film_batch_stride,
+                              int64_t n_points, int64_t points_per_batch, const float* narrow_in, int32_t narrow_width,
+                              const float* narrow_w, void* a_out, void* gate_out, int32_t dtype, void* stream) {
+    FN_REQUIRE(bias && film_layer && a_out && gate_out && n_points > 0 && points_per_batch > 0, "bad argument");
+    FN_REQUIRE(narrow_width == 0 || (narrow_in && narrow_w), "narrow inputs missing");
+    FN_REQUIRE(dtype == FENERF_DTYPE_F16 || dtype == FENERF_DTYPE_F32, "dtype");
+    return film_forward_stash(z, bias, film_layer, film_batch_stride, n_points, points_per_batch, narrow_in, narrow_width,
+                              narrow_w, a_out, gate_out, dtype, (cudaStream_t)stream);
+}
+
+int fenerf_gate_backward(void* dA, const void* gate, int64_t n_points, int64_t points_per_batch, float* colsum, int32_t dtype,
+                         void* stream) {
+    FN_REQUIRE(dA && gate && colsum && n_points > 0 && points_per_batch > 0, "bad argument");
+    FN_REQUIRE(dtype == FENERF_DTYPE_F16 || dtype == FENERF_DTYPE_F32, "dtype");
+    return gate_backward(dA, gate, n_points, points_per_batch, colsum, dtype, (cudaStream_t)stream);
+}
+
+int fenerf_head_grads(const float* d_raw, const float* raw, int64_t n_points, int32_t out_dim, int32_t label_dim,
+                      const float* scale, void* d_heads, void* d_rgb, int32_t dtype, void* stream) {
+    FN_REQUIRE(d_raw && raw && scale && d_heads && d_rgb && n_points > 0, "bad argument");
+    FN_REQUIRE(dtype == FENERF_DTYPE_F16 || dtype == FENERF_DTYPE_F32, "dtype");
+    return head_grads(d_raw, raw, n_points, out_dim, label_dim, scale, d_heads, d_rgb, dtype, (cudaStream_t)stream);
+}
+
+int fenerf_extras_gather(const fenerf_field_desc* field, const void* packed, const float* points, const float* dirs,
+                         int64_t n_points, int64_t points_per_batch, int32_t dir_group, int32_t lock_dirs, float* out,
+                         void* stream) {
+    FnLayout L;
+    FN_REQUIRE(fn_make_layout(field, &L) == 0, "unsupported field description");
+    FN_REQUIRE(packed && points && dirs && out && n_points > 0 && points_per_batch > 0 && dir_group >= 1, "bad argument");
+    return extras_gather(L, (const unsigned char*)packed, points, dirs, n_points, points_per_batch, dir_group, lock_dirs, out,
+                         (cudaStream_t)stream);
+}
+
+int fenerf_grid_scatter_add(const fenerf_field_desc* field, const float* points, const void* d_feat, int32_t ld,
+                            int64_t n_points, float* grad_channels_last, int32_t dtype, void* stream) {
+    FnLayout L;
+    FN_REQUIRE(fn_make_layout(field, &L) == 0, "unsupported field description");
+    FN_REQUIRE(points && d_feat && grad_channels_last && n_points > 0 && ld >= 32 && ld % 8 == 0, "bad argument");
+    FN_REQUIRE(dtype == FENERF_DTYPE_F16 || dtype == FENERF_DTYPE_F32, "dtype");
+    return grid_scatter_add(L, points, d_feat, ld, n_points, grad_channels_last, dtype, (cudaStream_t)stream);
+}
+
+int fenerf_grid_unpack_grad(const fenerf_field_desc* field, const float* grad_channels_last, float* out,
+                            const float* inv_scale, void* stream) {
+    FnLayout L;
+    FN_REQUIRE(fn_make_layout(field, &L) == 0 && L.grid_channels > 0, "field has no grid");
+    FN_REQUIRE(grad_channels_last && out && inv_scale, "bad argument");
+    return grid_unpack_grad(L, grad_channels_last, out, inv_scale, (cudaStream_t)stream);
 }
 
 #pragma GCC visibility pop

@@ -106,4 +106,20 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
               const float* z_f, const float* noise, float* pixels, float* depth, float* wsum, float* weights,
               int32_t* sort_idx, cudaStream_t st);
 
+// backward.cu
+int composite_backward(const fenerf_render_desc* rd, int C, const float* raw_c, const float* z_c, const float* raw_f,
+                       const float* z_f, const float* noise, const float* d_pixels, float* d_raw_c, float* d_raw_f,
+                       cudaStream_t st);
+int film_forward_stash(const float* z, const float* bias, const float* film_layer, long long film_batch_stride, long long P,
+                       long long ppb, const float* xin, int kx, const float* wx, void* a_out, void* gate_out, int f32,
+                       cudaStream_t st);
+int gate_backward(void* dA, const void* gate, long long P, long long ppb, float* colsum, int f32, cudaStream_t st);
+int head_grads(const float* d_raw, const float* raw, long long P, int C, int L, const float* scale, void* dH, void* dRGB,
+               int f32, cudaStream_t st);
+int extras_gather(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs, long long P,
+                  long long ppb, int dir_group, int lock_dirs, float* out, cudaStream_t st);
+int grid_scatter_add(const FnLayout& L, const float* points, const void* d_feat, int ld, long long P, float* grad_cl,
+                     int f32, cudaStream_t st);
+int grid_unpack_grad(const FnLayout& L, const float* grad_cl, float* out, const float* inv_scale, cudaStream_t st);
+
 }  // namespace fn

@@ -30,6 +30,7 @@ class _RenderSkeleton:
         if device.type != 'cuda':
             raise RuntimeError("fenerf_b200 renders on CUDA only; move the generator to a B200 (got %s)" % device)
         rng = kwargs.get('_rng') or vr.DeviceRng(device)
+        with_grad = (not staged) and ops.needs_grad(self.siren, film)
         if staged:
             # EMA copy_to / restore write through .data: fingerprint-check the packed weights (host sync; the
             # staged methods end in .cpu() anyway)
@@ -60,13 +61,20 @@ class _RenderSkeleton:
             debug = kwargs.get('_debug')
             fill_mode = kwargs.get('fill_mode', None) if staged else None
             wants_per_sample_weights = staged and fill_mode in (None, 'debug', 'seg_padding_background')
-            pixels, depth, wsum, weights, inds = ops.render_forward(
-                self.siren, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb.contiguous(),
-                rng_noise_c, rng_u, rng_noise_f, want_depth=staged or debug is not None,
-                want_weights_sum=staged or debug is not None, want_weights=wants_per_sample_weights,
-                want_inds=debug is not None)
-            if debug is not None:
-                debug.update(depth=depth, weights_sum=wsum, inds=inds, pitch=pitch, yaw=yaw, cam2world=cam2world)
+            if not with_grad:
+                pixels, depth, wsum, weights, inds = ops.render_forward(
+                    self.siren, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb.contiguous(),
+                    rng_noise_c, rng_u, rng_noise_f, want_depth=staged or debug is not None,
+                    want_weights_sum=staged or debug is not None, want_weights=wants_per_sample_weights,
+                    want_inds=debug is not None)
+                if debug is not None:
+                    debug.update(depth=depth, weights_sum=wsum, inds=inds, pitch=pitch, yaw=yaw, cam2world=cam2world)
+        if with_grad:
+            # the differentiable call (G step, inversion): same kernels forward, backward in fenerf_b200/backward.py
+            from .. import backward
+            pixels = backward.render_with_grad(self.siren, rd, film, x_lin, y_lin, z_lin, cam2world,
+                                               rng_perturb.contiguous(), rng_noise_c, rng_u, rng_noise_f)
+            depth = wsum = weights = None
         return pixels, depth, wsum, weights, pitch, yaw
 
     def _check_no_neural_renderer(self):
@@ -120,11 +128,6 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
         if 'img_feat_size' in kwargs:
             img_size = kwargs['img_feat_size']
         self._check_no_neural_renderer()
-        if ops.needs_grad(self.siren, z):
-            from .. import autograd_path
-            return autograd_path.generator_forward(self, (z,), img_size, fov, ray_start, ray_end, num_steps, h_stddev,
-                                                   v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist,
-                                                   lock_view_dependence, kwargs)
         frequencies, phase_shifts = self.siren.mapping_network(z)
         pixels, _, _, _, pitch, yaw = self._render(
             self._film(frequencies, phase_shifts), z.shape[0], img_size, fov, ray_start, ray_end, num_steps, h_stddev,
@@ -175,11 +178,6 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
         if 'img_feat_size' in kwargs:
             img_size = kwargs['img_feat_size']
         self._check_no_neural_renderer()
-        if ops.needs_grad(self.siren, frequencies, phase_shifts):
-            from .. import autograd_path
-            return autograd_path.generator_forward_with_frequencies(
-                self, (frequencies, phase_shifts), img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev,
-                h_mean, v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs)
         pixels, _, _, _, pitch, yaw = self._render(
             self._film(frequencies, phase_shifts), frequencies.shape[0], img_size, fov, ray_start, ray_end, num_steps,
             h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs,
@@ -229,11 +227,6 @@ class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
             return self.part_forward(z_geo, z_app, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev,
                                      h_mean, v_mean, hierarchical_sample, sample_dist=None,
                                      lock_view_dependence=False, **kwargs)
-        if ops.needs_grad(self.siren, z_geo, z_app):
-            from .. import autograd_path
-            return autograd_path.generator_forward(self, (z_geo, z_app), img_size, fov, ray_start, ray_end, num_steps,
-                                                   h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample,
-                                                   sample_dist, lock_view_dependence, kwargs)
         film = self.siren.film_table(*self._map(z_geo, z_app))
         pixels, _, _, _, pitch, yaw = self._render(
             film, batch_size, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean,
@@ -285,12 +278,6 @@ class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
                                  fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean,
                                  hierarchical_sample, sample_dist=None, lock_view_dependence=False, **kwargs):
         batch_size = frequencies_app.shape[0]
-        if ops.needs_grad(self.siren, frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app):
-            from .. import autograd_path
-            return autograd_path.generator_forward_with_frequencies(
-                self, (frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app), img_size, fov, ray_start,
-                ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist,
-                lock_view_dependence, kwargs)
         film = self.siren.film_table(frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app)
         pixels, _, _, _, pitch, yaw = self._render(
             film, batch_size, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean,

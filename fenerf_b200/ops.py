@@ -97,9 +97,6 @@ def siren_points(module, points, film, ray_directions, precision=None, dir_group
     1509-1530).  Forward-only: differentiating through it is section 8f-1 of SURVEY.md.
     """
     if needs_grad(module, points, film):
-        if autograd_opted_in():
-            from . import autograd_path
-            return autograd_path.siren_points_torch(module, points, film, ray_directions)
         raise NotImplementedError(GRAD_MESSAGE)
     packed = module.packed()
     device = packed.device
@@ -129,13 +126,9 @@ def siren_points(module, points, film, ray_directions, precision=None, dir_group
     return out
 
 
-GRAD_MESSAGE = ("fenerf_b200: backward through the fused render is not built yet (SURVEY.md 8f-1); wrap the call "
-                "in torch.no_grad(), or set FENERF_B200_TORCH_AUTOGRAD=1 to route grad-requiring calls through "
-                "the torch-op formulation (fenerf_b200/autograd_path.py)")
-
-
-def autograd_opted_in():
-    return os.environ.get("FENERF_B200_TORCH_AUTOGRAD", "0") == "1"
+GRAD_MESSAGE = ("fenerf_b200: the point-network entry (<SIREN>.forward / forward_with_frequencies_phase_shifts) is "
+                "forward-only; differentiate through the generator's forward / forward_with_frequencies "
+                "(fenerf_b200/backward.py), or wrap the call in torch.no_grad()")
 
 
 def needs_grad(module, *tensors):
@@ -300,3 +293,39 @@ def render_forward(module, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb
             inds.data_ptr() if inds is not None else 0, ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()),
             _stream(device)))
     return pixels, depth, wsum, weights, inds
+
+
+def render_forward_stages(module, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb, rng_noise_c, rng_u, rng_noise_f):
+    """fenerf_render_forward into a PRIVATE workspace, returned together with typed views of the intermediates
+    it leaves there (fenerf_workspace_layout): what the backward consumes (fenerf_b200/backward.py)."""
+    packed = module.packed()
+    device = packed.device
+    lib = _lib.lib()
+    b, n, s = rd.batch, rd.img_h * rd.img_w, rd.num_steps
+    c = packed.desc.out_dim
+    film = _prep(film, device)
+    pixels = torch.empty((b, c - 1, rd.img_h, rd.img_w), dtype=torch.float32, device=device)
+    off = _lib.WorkspaceOffsets()
+    with torch.cuda.device(device):
+        _lib.check(lib.fenerf_workspace_layout(C.byref(rd), C.byref(packed.desc), C.byref(off)))
+        ws = torch.empty(off.total + 256, dtype=torch.uint8, device=device)
+        base = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr()
+        _lib.check(lib.fenerf_render_forward(
+            C.byref(rd), C.byref(packed.desc), packed.ptr, _chk(film, "film", device),
+            _chk(x_lin, "x_lin", device), _chk(y_lin, "y_lin", device), _chk(z_lin, "z_lin", device),
+            _chk(cam2world, "cam2world", device), _chk(rng_perturb, "rng_perturb", device),
+            _chk(rng_noise_c, "rng_noise_c", device), _chk(rng_u, "rng_u", device), _chk(rng_noise_f, "rng_noise_f", device),
+            pixels.data_ptr(), 0, 0, 0, 0, ws.data_ptr() + base, ws.numel() - base, _stream(device)))
+
+    def view(offset, shape):
+        numel = 1
+        for d in shape:
+            numel *= d
+        return ws[base + offset: base + offset + numel * 4].view(torch.float32).view(shape)
+
+    st = dict(pixels=pixels, workspace=ws, points_c=view(off.points_coarse, (b, n, s, 3)), z_c=view(off.z_coarse, (b, n, s)),
+              dirs=view(off.dirs, (b, n, 3)), raw_c=view(off.raw_coarse, (b, n, s, c)), raw_f=None, z_f=None, points_f=None)
+    if rd.hierarchical:
+        st.update(points_f=view(off.points_fine, (b, n, s, 3)), z_f=view(off.z_fine, (b, n, s)),
+                  raw_f=view(off.raw_fine, (b, n, s, c)))
+    return st

@@ -224,6 +224,23 @@ int fenerf_composite(const fenerf_render_desc* rd, int32_t out_dim, const float*
 /* Scratch bytes fenerf_render_forward needs for this (render, field) pair. */
 size_t fenerf_workspace_bytes(const fenerf_render_desc* rd, const fenerf_field_desc* field);
 
+/* Where fenerf_render_forward leaves its intermediates inside the caller's workspace (byte offsets): the sample
+ * points and depths of both passes, ray directions / origins and the raw field outputs -- what the backward
+ * needs, and what a debugger wants to look at.  Valid after a fenerf_render_forward with the same (rd, field);
+ * the fine entries only when rd->hierarchical. */
+typedef struct fenerf_workspace_offsets {
+    size_t points_coarse;  /* (B,N,S,3) */
+    size_t z_coarse;       /* (B,N,S)   */
+    size_t dirs;           /* (B,N,3)   */
+    size_t origins;        /* (B,3)     */
+    size_t raw_coarse;     /* (B,N,S,C) after the GUARD refinement */
+    size_t z_fine;         /* (B,N,S)   */
+    size_t points_fine;    /* (B,N,S,3) */
+    size_t raw_fine;       /* (B,N,S,C) */
+    size_t total;
+} fenerf_workspace_offsets;
+int fenerf_workspace_layout(const fenerf_render_desc* rd, const fenerf_field_desc* field, fenerf_workspace_offsets* out);
+
 /* The whole per-batch render: ray_setup -> field(coarse) -> resample -> field(fine) -> composite.
  * Replaces the body of ImplicitGenerator3d.forward / DoubleImplicitGenerator3d.forward after the
  * mapping network (generators/generators.py:41-104, 465-527) and the chunked loops of
@@ -240,6 +257,60 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
                           float* pixels, float* depth, float* weights_sum, float* weights,
                           int64_t* inds_dbg, void* workspace, size_t workspace_bytes,
                           void* stream);
+
+/* ---- backward of the render ---------------------------------------------------------------------
+ * What the reference differentiates (train_double_latent_semantic.py:405-446 G step,
+ * inverse_render_double_semantic.py:385-407 inversion through forward_with_frequencies,
+ * generators/generators.py:735-798): the final fancy_integration over the merged samples and both
+ * point-network passes; ray set-up and resampling are no_grad there (generators.py:41, 59).
+ * The host mirror (fenerf_b200/backward.py, a torch.autograd.Function) chains these entry points with the
+ * plain 256-wide library GEMMs between them.                                                          */
+
+/* element type of the backward's activation / gradient streams: fp16 (tensor-core GEMMs between the kernels, the
+ * default) or fp32 (the parity mode that goes with FENERF_PRECISION_EXACT) */
+#define FENERF_DTYPE_F16 0
+#define FENERF_DTYPE_F32 1
+
+/* d pixels (B, C-1, H, W) -> d raw outputs.  Backward of the merge + fancy_integration + softmax / *2-1
+ * epilogue (generators.py:85-104, volumetric_rendering.py:18-50); same arguments as fenerf_composite.
+ * d_raw_fine / raw_fine / z_fine NULL when !hierarchical.  fill modes are staged_forward-only (no_grad). */
+int fenerf_composite_backward(const fenerf_render_desc* rd, int32_t out_dim, const float* raw_coarse,
+                              const float* z_coarse, const float* raw_fine, const float* z_fine,
+                              const float* rng_noise, const float* d_pixels,
+                              float* d_raw_coarse, float* d_raw_fine, void* stream);
+
+/* One FiLM layer's forward values for the backward (siren/siren.py:113-123): from the GEMM output
+ * z (n_points, 256) fp32 (NULL for the first layer) plus optional narrow inputs narrow_in (n_points, w) fp32
+ * against narrow_w (256, w) fp32 (positions; [dir, grid features] of the first colour layer):
+ *   a = sin(f (z + bias) + p)  -> a_out (n_points, 256);   gate = f cos(f (z + bias) + p) -> gate_out   (both of `dtype`)
+ * film_layer points at image 0's [2][256] block of the layer, film_batch_stride floats between images. */
+int fenerf_film_forward_stash(const float* z, const float* bias, const float* film_layer, int64_t film_batch_stride,
+                              int64_t n_points, int64_t points_per_batch, const float* narrow_in, int32_t narrow_width,
+                              const float* narrow_w, void* a_out, void* gate_out, int32_t dtype, void* stream);
+
+/* dZ = dA * gate in place ((n_points, 256) of `dtype`); colsum (B, 256) fp32 += per-image column sums of dZ
+ * (= d bias; d phase = colsum / f; d freq follows from the per-image dW, see csrc/backward.cu). */
+int fenerf_gate_backward(void* dA, const void* gate, int64_t n_points, int64_t points_per_batch, float* colsum,
+                         int32_t dtype, void* stream);
+
+/* d raw (n_points, C) -> scaled head gradients of `dtype`: d_heads (n_points, 32) = [d labels.., d sigma, 0..],
+ * d_rgb (n_points, 8) = [d rgb * rgb (1 - rgb), 0..]; `scale` is a DEVICE scalar (power of two). */
+int fenerf_head_grads(const float* d_raw, const float* raw, int64_t n_points, int32_t out_dim, int32_t label_dim,
+                      const float* scale, void* d_heads, void* d_rgb, int32_t dtype, void* stream);
+
+/* out (n_points, 3 + G) fp32 = [ray direction, trilinear grid features]: the narrow inputs of the first colour
+ * layer (siren.py:1519-1522), from the packed channels-last grid. */
+int fenerf_extras_gather(const fenerf_field_desc* field, const void* packed, const float* points, const float* dirs,
+                         int64_t n_points, int64_t points_per_batch, int32_t dir_group, int32_t lock_dirs, float* out,
+                         void* stream);
+
+/* Backward of sample_from_3dgrid (siren.py:314-330): d features (n_points, ld >= 32) of `dtype` scattered with the
+ * trilinear weights into grad_channels_last [R][R][R][32] fp32 (vector atomics); then the transpose back to
+ * torch's (1, G, R, R, R) layout, multiplied by the DEVICE scalar *inv_scale. */
+int fenerf_grid_scatter_add(const fenerf_field_desc* field, const float* points, const void* d_feat, int32_t ld,
+                            int64_t n_points, float* grad_channels_last, int32_t dtype, void* stream);
+int fenerf_grid_unpack_grad(const fenerf_field_desc* field, const float* grad_channels_last, float* out,
+                            const float* inv_scale, void* stream);
 
 /* Per-thread message for the last non-zero return. */
 const char* fenerf_last_error(void);

@@ -180,3 +180,9 @@ def loss_weights(shape):
     """Fixed projection of rendered frames to a scalar for the gradient goldens: L = sum(pixels * W)."""
     g = torch.Generator().manual_seed(99)
     return torch.randn(shape, generator=g)
+
+
+def grid_probe_index(numel, n):
+    """Fixed pseudo-random flat indices into the feature grid (the gradient goldens store only these entries)."""
+    g = torch.Generator().manual_seed(7)
+    return torch.randint(0, numel, (n,), generator=g)

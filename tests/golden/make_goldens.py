@@ -79,7 +79,7 @@ def main():
 
 
 # ---- gradients of the differentiable call (the reference's G step / inversion path) -----------------
-GRAD_CASES = ("a_small", "d_small")
+GRAD_CASES = ("a_small", "d_small", "b_small", "d_staged_softmax", "a_hier_softplus")
 #: parameters whose gradients are stored (a cross-section of trunk, heads, colour branch, mapping network)
 GRAD_PARAMS = {
     "A": ["siren.network.0.layer.weight", "siren.network.7.layer.bias", "siren.final_layer.weight",
@@ -89,7 +89,14 @@ GRAD_PARAMS = {
           "siren.color_layer_sine.2.layer.bias", "siren.color_layer_linear.0.weight",
           "siren.label_layer_linear.1.weight", "siren.geo_mapping_network.network.8.bias",
           "siren.app_mapping_network.network.8.bias"],
+    "B": ["siren.network.0.layer.weight", "siren.network.3.layer.weight", "siren.network.7.layer.bias",
+          "siren.final_layer.weight", "siren.final_layer.bias", "siren.color_layer_sine.0.layer.weight",
+          "siren.color_layer_sine.2.layer.bias", "siren.color_layer_linear.0.weight", "siren.color_layer_linear.0.bias",
+          "siren.label_layer_linear.0.weight", "siren.label_layer_linear.1.bias", "siren.label_layer_linear.2.weight",
+          "siren.geo_mapping_network.network.8.bias", "siren.app_mapping_network.network.8.bias"],
 }
+#: model B's grid gradient is 113 MB: stored as a fixed random projection (and its abs-sum)
+GRID_PROBE = 4096
 
 
 def grad_goldens():
@@ -102,7 +109,8 @@ def grad_goldens():
         gen, _ = build_reference(case, ref_generators, ref_siren)
         latents = tuple(z.clone().requires_grad_(True) for z in _cases.make_latents(case))
         torch.manual_seed(case.seed)
-        pixels, _ = gen(*latents, **_cases.reference_kwargs(case))
+        kw = {k: v for k, v in case.cfg.items() if k != "fill_mode"}      # forward() of a staged case: same config
+        pixels, _ = gen(*latents, **kw)
         loss = (pixels * _cases.loss_weights(pixels.shape)).sum()
         loss.backward()
         params = dict(gen.named_parameters())
@@ -111,14 +119,49 @@ def grad_goldens():
             out["latent%d" % i] = z.grad.numpy()
         for k in GRAD_PARAMS[case.model]:
             out[k] = params[k].grad.numpy()
+        if "siren.spatial_embeddings" in params:
+            g = params["siren.spatial_embeddings"].grad.reshape(-1)
+            idx = _cases.grid_probe_index(g.numel(), GRID_PROBE)
+            out["grid_probe"] = g[idx].numpy()
+            out["grid_abs_sum"] = np.array(g.abs().sum().item())
         path = os.path.join(out_dir, "grad_%s.npz" % name)
         np.savez_compressed(path, **out)
         print("%-28s loss %.6f  %d gradient tensors -> %s (%.1f KB)" % (
             name, loss.item(), len(out) - 1, os.path.basename(path), os.path.getsize(path) / 1024))
 
 
+def frequency_grad_goldens():
+    """tests/golden/gradfreq_a_small.npz: the inversion call -- d L / d (frequencies, phase_shifts) through
+    forward_with_frequencies (inverse_render_double_semantic.py:385-407, generators.py:353-431)."""
+    ref_generators, ref_siren, _ = ref_shim.load()
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for name in ("a_small", "d_small"):
+        case = _cases.CASE_BY_NAME[name]
+        gen, _ = build_reference(case, ref_generators, ref_siren)
+        latents = _cases.make_latents(case)
+        with torch.no_grad():
+            if case.model == "A":
+                fp = list(gen.siren.mapping_network(latents[0]))
+            else:
+                fg, pg = gen.siren.geo_mapping_network(latents[0])
+                fa, pa = gen.siren.app_mapping_network(latents[1])
+                fp = [fg, fa, pg, pa]
+        fp = [t.clone().requires_grad_(True) for t in fp]
+        torch.manual_seed(case.seed)
+        pixels, _ = gen.forward_with_frequencies(*fp, **case.cfg)
+        loss = (pixels * _cases.loss_weights(pixels.shape)).sum()
+        loss.backward()
+        out = {"loss": np.array(loss.item())}
+        for i, t in enumerate(fp):
+            out["arg%d" % i] = t.grad.numpy()
+        path = os.path.join(out_dir, "gradfreq_%s.npz" % name)
+        np.savez_compressed(path, **out)
+        print("%-28s loss %.6f -> %s (%.1f KB)" % (name, loss.item(), os.path.basename(path), os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     if sys.argv[1:2] == ["--grads"]:
         grad_goldens()
+        frequency_grad_goldens()
     else:
         main()

@@ -292,42 +292,141 @@ def test_extra_curriculum_kwargs_are_swallowed_and_max_batch_size_ignored():
     assert px2.shape == (1, 3, 16, 16) and depth.shape == (1, 16, 16) and not depth.is_cuda
 
 
-def test_grad_requiring_call_fails_loudly_without_opt_in(monkeypatch):
-    monkeypatch.delenv("FENERF_B200_TORCH_AUTOGRAD", raising=False)
-    case = _cases.CASE_BY_NAME["a_small"]
-    gen = _cases.build_mirror(case, DEV)
-    with pytest.raises(NotImplementedError):
-        gen(torch.randn(1, 256, device=DEV), **case.cfg)
+#: d sigma carries relu'(sigma) (volumetric_rendering.py:32): a step at sigma = 0.  A sample whose density the two
+#: implementations place on different sides of 0 (|sigma| below the forward's own error: 5e-5 exact, 3e-4 fp16; a
+#: random-init double-latent field has |sigma| ~ 1e-3) switches its whole contribution on or off.  Every gradient
+#: sees a little of that; the density head's own weight gradient is nothing but that sum, so it gets the bound of
+#: the flipped fraction instead of the rounding bound (the softplus case below has no kink and no exception).
+KINK_KEYS = ("siren.final_layer.weight", "siren.final_layer.bias")
 
 
-@pytest.mark.parametrize("name", ["a_small", "d_small"])
-def test_opt_in_autograd_path_matches_reference_gradients(monkeypatch, name):
-    """FENERF_B200_TORCH_AUTOGRAD=1 (fenerf_b200/autograd_path.py: CUDA ray set-up / resampling, torch ops for
-    the differentiable stages) against the reference's own autograd: d sum(pixels * W) / d (latents, weights),
-    stored by tests/golden/make_goldens.py --grads."""
+def _compare_grads(gold, got, rel=2e-3, kink_rel=None):
+    worst = {}
+    for key in gold.files:
+        if key in ("loss", "grid_probe", "grid_abs_sum"):
+            continue
+        want = torch.from_numpy(gold[key])
+        have = got[key].detach().cpu().float()
+        scale = want.abs().max().item()
+        assert scale > 0, key
+        worst[key] = (have - want).abs().max().item() / scale
+    bad = {k: "%.2e" % v for k, v in worst.items() if not v <= (kink_rel if (kink_rel and k in KINK_KEYS) else rel)}
+    assert not bad, "gradients beyond %.0e of their tensor's max: %s   (all: %s)" % (
+        rel, bad, {k: "%.1e" % v for k, v in worst.items()})
+    return worst
+
+
+@pytest.mark.parametrize("name,precision", [("a_small", "exact"), ("b_small", "exact"), ("d_staged_softmax", "exact"),
+                                            ("a_hier_softplus", "exact"), ("a_small", "guard"), ("d_small", "guard"),
+                                            ("b_small", "guard"), ("d_staged_softmax", "guard"), ("a_hier_softplus", "guard")])
+def test_backward_matches_reference_gradients(runs, name, precision):
+    """The differentiable call (train_double_latent_semantic.py:411-446) against the reference's own autograd:
+    d sum(pixels * W) / d (latents, field weights, mapping networks, feature grid), stored by
+    tests/golden/make_goldens.py --grads.  Backward = fenerf_b200/backward.py over the CUDA library."""
+    import dataclasses
     import os
-    monkeypatch.setenv("FENERF_B200_TORCH_AUTOGRAD", "1")
     case = _cases.CASE_BY_NAME[name]
-    run = _harness.oracle_run(case)            # the reference's draws for this seed
+    if case.method != "forward":
+        # the gradient goldens come from forward() under manual_seed(case.seed): no avg-frequency draws first
+        case = dataclasses.replace(case, method="forward", cfg={k: v for k, v in case.cfg.items() if k != "fill_mode"})
+        run = _harness.oracle_run(case)
+    else:
+        case, run = runs(name)
     gold = np.load(os.path.join(_cases.GOLDEN_DIR, "grad_%s.npz" % name))
     gen = _cases.build_mirror(case, DEV)
     latents = [_cuda(z).requires_grad_(True) for z in run["latents"]]
-    pixels, _ = gen(*latents, **dict(case.cfg, _rng=ReplayRng(run["draws"], DEV)))
-    assert (pixels.detach().cpu() - run["out"]["pixels"]).abs().max() <= 2e-4
+    kw = {k: v for k, v in case.cfg.items() if k != "fill_mode"}
+    l0 = _lib.launch_count()
+    pixels, _ = gen(*latents, **dict(kw, _rng=ReplayRng(run["draws"], DEV), precision=precision))
+    assert pixels.requires_grad
+    if case.method == "forward":
+        assert (pixels.detach().cpu() - run["out"]["pixels"]).abs().max() <= 1e-3
     loss = (pixels * _cases.loss_weights(pixels.shape).to(DEV)).sum()
     assert abs(loss.item() - float(gold["loss"])) <= 2e-3 * max(1.0, abs(float(gold["loss"])))
     loss.backward()
+    assert _lib.launch_count() - l0 > 20, "the backward did not go through the CUDA library"
     got = {"latent%d" % i: z.grad for i, z in enumerate(latents)}
     got.update({k: p.grad for k, p in gen.named_parameters()})
-    for key in gold.files:
-        if key == "loss":
-            continue
-        want = torch.from_numpy(gold[key])
-        have = got[key].detach().cpu()
-        scale = want.abs().max().item()
-        assert scale > 0, key
-        assert (have - want).abs().max().item() <= 2e-3 * scale, "gradient of %s: max diff %g vs scale %g" % (
-            key, (have - want).abs().max().item(), scale)
+    # exact mode (fp32 streams, fp32 GEMMs) pins the algorithm; the default runs its activation / gradient
+    # streams in fp16 between the tensor-core GEMMs (what the reference's own AMP training does,
+    # train_double_latent_semantic.py:408): gate = f cos(f z + p) with f ~ 30-50 amplifies the 3e-4 of a
+    # recomputed z into ~1e-2 of phase, so individual entries sit within 1e-2 of the tensor's largest entry
+    relu = case.cfg["clamp_mode"] == "relu"
+    if precision == "exact":
+        _compare_grads(gold, got, rel=5e-4, kink_rel=1e-2 if relu else None)
+    else:
+        _compare_grads(gold, got, rel=2e-2, kink_rel=0.3 if relu else None)
+    if "grid_probe" in gold.files:
+        g = gen.siren.spatial_embeddings.grad.reshape(-1).cpu()
+        idx = _cases.grid_probe_index(g.numel(), len(gold["grid_probe"]))
+        want = torch.from_numpy(gold["grid_probe"])
+        gscale = max(want.abs().max().item(), float(gold["grid_abs_sum"]) / g.numel() * 50)
+        assert (g[idx] - want).abs().max() <= 1e-2 * gscale
+        assert abs(g.abs().sum().item() - float(gold["grid_abs_sum"])) <= 5e-3 * float(gold["grid_abs_sum"])
+
+
+@pytest.mark.parametrize("name", ["a_small", "d_small"])
+def test_inversion_gradients_through_forward_with_frequencies(runs, name):
+    """inverse_render_double_semantic.py:385-407: gradients w.r.t. the FiLM frequencies / phase shifts."""
+    import os
+    case, run = runs(name)
+    gold = np.load(os.path.join(_cases.GOLDEN_DIR, "gradfreq_%s.npz" % name))
+    gen = _cases.build_mirror(case, DEV)
+    with torch.no_grad():
+        if case.model == "A":
+            fp = list(gen.siren.mapping_network(_cuda(run["latents"][0])))
+        else:
+            fg, pg = gen.siren.geo_mapping_network(_cuda(run["latents"][0]))
+            fa, pa = gen.siren.app_mapping_network(_cuda(run["latents"][1]))
+            fp = [fg, fa, pg, pa]
+    fp = [t.clone().requires_grad_(True) for t in fp]
+    for p in gen.parameters():
+        p.requires_grad_(False)                       # the inversion optimises the offsets only
+    pixels, _ = gen.forward_with_frequencies(*fp, **dict(case.cfg, _rng=ReplayRng(run["draws"], DEV), precision="exact"))
+    loss = (pixels * _cases.loss_weights(pixels.shape).to(DEV)).sum()
+    loss.backward()
+    _compare_grads(gold, {"arg%d" % i: t.grad for i, t in enumerate(fp)}, rel=5e-4)
+    assert all(p.grad is None for p in gen.parameters())
+
+
+def test_backward_under_autocast_and_gradscaler():
+    """The G step runs under torch.cuda.amp.autocast with a GradScaler (train_double_latent_semantic.py:405-446):
+    the render node casts its inputs to fp32, returns fp32 pixels and survives a 2^16-scaled upstream gradient."""
+    case = _cases.CASE_BY_NAME["a_small"]
+    gen = _cases.build_mirror(case, DEV)
+    z = torch.randn(2, 256, device=DEV)
+    w = _cases.loss_weights((2, 3, 16, 16)).to(DEV)
+    torch.manual_seed(3)
+    px, _ = gen(z, **case.cfg)
+    (px * w).sum().backward()
+    ref = {k: p.grad.clone() for k, p in gen.named_parameters()}
+    gen.zero_grad()
+    scaler = torch.amp.GradScaler("cuda", init_scale=65536.0)
+    torch.manual_seed(3)
+    with torch.autocast("cuda", dtype=torch.float16):
+        px2, _ = gen(z, **case.cfg)
+        assert px2.dtype == torch.float32
+        loss = (px2 * w).sum()
+    scaler.scale(loss).backward()
+    for k, p in gen.named_parameters():
+        if "mapping_network" in k:
+            continue                                   # the mapping network itself runs in fp16 under autocast
+        got = p.grad / 65536.0
+        scale = ref[k].abs().max().item()
+        # loose on purpose: under autocast the mapping network's Linears run in fp16, so the two renders do not even
+        # share their FiLM table to better than 1e-3; what is checked is dtype handling and the unscaling
+        assert (got - ref[k]).abs().max().item() <= 0.2 * scale + 1e-12, k
+
+
+def test_point_network_entry_is_forward_only():
+    case = _cases.CASE_BY_NAME["a_small"]
+    gen = _cases.build_mirror(case, DEV)
+    pts = torch.randn(1, 64, 3, device=DEV) * 0.1
+    with pytest.raises(NotImplementedError):
+        gen.siren(pts, torch.randn(1, 256, device=DEV), ray_directions=torch.randn(1, 64, 3, device=DEV))
+    with torch.no_grad():
+        out = gen.siren(pts, torch.randn(1, 256, device=DEV), ray_directions=torch.randn(1, 64, 3, device=DEV))
+    assert out.shape == (1, 64, 4)
 
 
 def test_ema_style_data_copy_is_seen_by_staged_forward():
