@@ -2,7 +2,7 @@
 """bench.py -- rendered faces/sec of the FENeRF volumetric render hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model A|B]
-                    [--precision guard|fast|exact]
+                    [--precision guard|fast|exact] [--no-graph] [--quick]
 
 A "step" is one pass of the hot path over one batch of synthetic latents: BASELINE.json configs[1]
 -- 128x128 image, 24 (+24 hierarchical) samples per ray, batch 4 per GPU, forward-only -- through
@@ -206,122 +206,254 @@ def workload_config(args, world):
                 MODEL_NAME[args.model], IMG, IMG, STEPS_PER_RAY, STEPS_PER_RAY, BATCH_PER_GPU),
             "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d (images sharded, one frame all-gather)" % world,
             "precision_mode": args.precision,
-            "l2_policy": "inputs_larger_than_l2 (per-step working set ~200 MB of samples/raw outputs vs 126 MB L2; "
-                         "fresh latents and RNG draws every step)"}
+            "l2_policy": "inputs_larger_than_l2 (per-step working set ~140 MB of RNG draws, sample points and raw outputs vs "
+                         "126 MB L2; fresh latents and RNG draws every step, also under graph replay)"}
 
 
 # ------------------------------------------------------------------------------------------------
+class StepRunner:
+    """One model's render step in both arms (inputs resident / end to end), eager or as a captured CUDA graph."""
+
+    def __init__(self, args, model, world, rank, device, n_batches, precision=None, use_graph=True):
+        from fenerf_b200.dist import FrameGatherer
+        from fenerf_b200.graphs import GraphedRender
+        self.args, self.model, self.world, self.rank, self.device = args, model, world, rank, device
+        self.precision = precision or args.precision
+        self.gen = build_generator(model, device)
+        self.md = dict(metadata(), precision=self.precision)
+        B = BATCH_PER_GPU
+        self.B = B
+        self.C_img = self.gen.output_dim - 1
+        self.lat_host = [tuple(z.pin_memory() for z in zs) for zs in make_latents(model, n_batches, B, 1000 + 97 * rank)]
+        self.lat_dev = [tuple(z.to(device) for z in zs) for zs in self.lat_host]
+        self.gatherer = FrameGatherer(B, self.C_img, IMG, device)
+        self.out_host = [torch.empty((world * B, self.C_img, IMG, IMG), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.out_done = [torch.cuda.Event() for _ in range(2)]
+        self.frames_ready = [torch.cuda.Event() for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.host_sink = 0.0
+        self.first_e2e = 0
+        self.graph = None
+        if use_graph:
+            with torch.no_grad():
+                self.graph = GraphedRender(self.gen, self.lat_dev[0], self.md)
+
+    def render(self, latents):
+        if self.graph is not None:
+            return self.graph(*latents)[0]
+        with torch.no_grad():
+            return self.gen(*latents, **self.md)[0]
+
+    def step_resident(self, i):
+        return self.gatherer.gather(self.render(self.lat_dev[i % len(self.lat_dev)]))
+
+    def step_e2e(self, i):
+        k = i % len(self.lat_host)
+        if i > self.first_e2e:
+            # the frame buffer is reused every step: wait (on the GPU) until the previous D2H has read it
+            torch.cuda.current_stream().wait_event(self.out_done[(i - 1) & 1])
+        if self.graph is not None:
+            frames = self.graph(*self.lat_host[k])                 # H2D straight into the captured input buffers
+            frames = frames[0]
+        else:
+            zs = tuple(z.to(self.device, non_blocking=True) for z in self.lat_host[k])
+            with torch.no_grad():
+                frames = self.gen(*zs, **self.md)[0]
+        allf = self.gatherer.gather(frames)
+        self.frames_ready[i & 1].record()
+        self.copy_stream.wait_event(self.frames_ready[i & 1])
+        with torch.cuda.stream(self.copy_stream):   # D2H on its own stream: the next step's kernels do not queue behind it
+            self.out_host[i & 1].copy_(allf, non_blocking=True)
+            self.out_done[i & 1].record()
+        # double-buffered serving loop: the host reads step i-1's frames while step i is queued; every step's
+        # frames reach the host and are read inside the timed region
+        if i > self.first_e2e:
+            self.read_frames(i - 1)
+
+    def read_frames(self, i):
+        self.out_done[i & 1].synchronize()
+        self.host_sink += float(self.out_host[i & 1][0, 0, 0, 0]) + float(self.out_host[i & 1][-1, -1, -1, -1])
+
+    def time_resident(self, steps, warmup):
+        from fenerf_b200 import _lib
+        for i in range(warmup):
+            self.step_resident(i)
+        barrier(self.world); torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            self.step_resident(warmup + i)
+        ev1.record()
+        torch.cuda.synchronize(); barrier(self.world)
+        ms = max_over_ranks(ev0.elapsed_time(ev1), self.device, self.world) / steps
+        return ms, _lib.launch_count() - l0
+
+    def time_e2e(self, steps, warmup):
+        n_pre = min(warmup, 2)
+        self.first_e2e = 0
+        for i in range(n_pre):
+            self.step_e2e(i)
+        if n_pre:
+            self.read_frames(n_pre - 1)
+        barrier(self.world); torch.cuda.synchronize()
+        self.first_e2e = warmup
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            self.step_e2e(warmup + i)
+        self.read_frames(warmup + steps - 1)            # the last step's frames, inside the timed region
+        ev1.record()
+        torch.cuda.synchronize(); barrier(self.world)
+        return max_over_ranks(ev0.elapsed_time(ev1), self.device, self.world) / steps
+
+    def launches_per_step(self):
+        """Kernels of libfenerf_b200 in one step (a replayed graph launches them without passing through the
+        library's host counter, so count them on an eager step)."""
+        from fenerf_b200 import _lib
+        l0 = _lib.launch_count()
+        with torch.no_grad():
+            self.gen(*self.lat_dev[0], **self.md)
+        torch.cuda.synchronize()
+        return int(_lib.launch_count() - l0)
+
+    def bytes_per_step(self):
+        return sum(z.numel() * 4 for z in self.lat_host[0]), self.out_host[0].numel() * 4
+
+
+def measure_model(args, model, world, rank, local, steps, warmup, precision=None, sustained_s=0.0, roofline=True):
+    device = torch.device("cuda", local)
+    n_batches = min(steps + warmup, 64)
+    r = StepRunner(args, model, world, rank, device, n_batches, precision=precision, use_graph=not args.no_graph)
+    ms_step, _ = r.time_resident(steps, warmup)
+    ms_e2e = r.time_e2e(steps, warmup)
+    B = BATCH_PER_GPU
+    h2d, d2h = r.bytes_per_step()
+    lps = r.launches_per_step()
+    out = {"model": MODEL_NAME[model], "precision_mode": r.precision, "value": world * B / (ms_step / 1e3), "unit": "faces/s",
+           "ms_per_step": ms_step, "cuda_graph": r.graph is not None,
+           "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "faces/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h,
+                   "pipeline": "pinned latents -> H2D -> render (one CUDA graph launch) -> frame all-gather -> D2H on a copy stream into "
+                               "double-buffered pinned memory; step i-1's frames are read on the host while step i runs"},
+           "gpu_launches_per_step": lps, "gpu_launches": lps * steps}
+    if sustained_s > 0:
+        # a >= 3 s run: long enough to leave the boost clock / reach the power limit (VERDICT r1, weak #8)
+        n = max(steps, int(sustained_s * 1e3 / ms_step) + 1)
+        sampler = ClockSampler(local) if rank == 0 else None
+        ms_long, _ = r.time_resident(n, 3)
+        clocks = sampler.stop() if sampler else None
+        out["sustained"] = {"steps": n, "seconds": ms_long * n / 1e3, "value": world * B / (ms_long / 1e3), "unit": "faces/s",
+                            "ms_per_step": ms_long, "clocks": clocks}
+    if roofline:
+        out["roofline"] = field_roofline(r.gen, args, model, r.precision, r.lat_dev[0], metadata(), device)
+    return out
+
+
+def measure_train_step(args, world, rank, local):
+    """BASELINE configs[2]-shaped generator work of one training iteration of
+    CelebA_double_semantic_texture_embedding_256_dim_96 (curriculums.py:132-177) on one GPU: batch 32 as batch_split 4 x 8
+    (train_double_latent_semantic.py:279-292, 334-347, 405-446): per split two no_grad renders (the fakes of the two
+    discriminator steps) and one differentiable render + backward; then Adam on the generator.  The discriminators are
+    outside the hot path: the loss is a fixed random projection of the frames."""
+    device = torch.device("cuda", local)
+    gen = build_generator("B", device)
+    gen.train()
+    R, S, BATCH, SPLIT = 64, 24, 32, 4
+    md = dict(metadata(R), precision=args.precision)
+    opt = torch.optim.Adam(gen.parameters(), lr=6e-5, betas=(0, 0.9))
+    scaler = torch.amp.GradScaler("cuda")
+    w = torch.randn((BATCH // SPLIT, gen.output_dim - 1, R, R), device=device) / (R * R)
+
+    def iteration():
+        for _ in range(2):
+            with torch.no_grad():
+                for _ in range(SPLIT):
+                    gen(torch.randn(BATCH // SPLIT, 256, device=device), torch.randn(BATCH // SPLIT, 256, device=device), **md)
+        opt.zero_grad(set_to_none=True)
+        for _ in range(SPLIT):
+            with torch.autocast("cuda", dtype=torch.float16):
+                px, _ = gen(torch.randn(BATCH // SPLIT, 256, device=device), torch.randn(BATCH // SPLIT, 256, device=device), **md)
+                loss = (px * w).sum()
+            scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(gen.parameters(), 10)
+        scaler.step(opt)
+        scaler.update()
+
+    for _ in range(2):
+        iteration()
+    torch.cuda.synchronize()
+    n = 5
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(n):
+        iteration()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / n
+    return {"workload": "cfg3-shaped: %s, %dx%d, %d+%d samples/ray, batch %d as %d x %d, per iteration 2 no_grad renders + "
+                        "1 differentiable render + backward per split, Adam step; synthetic loss (fixed projection of the frames)"
+                        % (MODEL_NAME["B"], R, R, S, S, BATCH, SPLIT, BATCH // SPLIT),
+            "ms_per_iteration": ms, "faces_rendered_per_iteration": 3 * BATCH, "rendered_faces_per_s": 3 * BATCH / (ms / 1e3),
+            "iterations_per_s": 1e3 / ms, "backward": "fenerf_b200/backward.py (CUDA kernels + library GEMMs), fp16 streams"}
+
+
 def run_ours(args, world, rank, local):
     from fenerf_b200 import _lib, ops
-    from fenerf_b200.dist import FrameGatherer
-    from fenerf_b200.generators import volumetric_rendering as vr
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     _lib.lib()
     ops.set_default_precision(args.precision)
-    gen = build_generator(args.model, device)
-    md = metadata()
-    B = BATCH_PER_GPU
-    C_img = gen.output_dim - 1
-    n_batches = args.steps + args.warmup
-    lat_host = [tuple(z.pin_memory() for z in zs) for zs in make_latents(args.model, n_batches, B, 1000 + 97 * rank)]
-    lat_dev = [tuple(z.to(device) for z in zs) for zs in lat_host]
-    gatherer = FrameGatherer(B, C_img, IMG, device)
-    out_host = [torch.empty((world * B, C_img, IMG, IMG), dtype=torch.float32).pin_memory() for _ in range(2)]
-    out_done = [torch.cuda.Event() for _ in range(2)]
-    frames_ready = [torch.cuda.Event() for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=device)
-    host_sink = [0.0]
     torch.manual_seed(4242 + rank)
-
-    def step_resident(i):
-        with torch.no_grad():
-            frames, _ = gen(*lat_dev[i], **md)
-        return gatherer.gather(frames)
-
-    def step_e2e(i):
-        if i > first_e2e[0]:
-            # the gathered-frame buffer is reused every step: wait (on the GPU) until the previous D2H has read it
-            torch.cuda.current_stream().wait_event(out_done[(i - 1) & 1])
-        zs = tuple(z.to(device, non_blocking=True) for z in lat_host[i])
-        with torch.no_grad():
-            frames, _ = gen(*zs, **md)
-        allf = gatherer.gather(frames)
-        frames_ready[i & 1].record()
-        copy_stream.wait_event(frames_ready[i & 1])
-        with torch.cuda.stream(copy_stream):        # D2H on its own stream: the next step's kernels do not queue behind it
-            out_host[i & 1].copy_(allf, non_blocking=True)
-            out_done[i & 1].record()
-        # double-buffered serving loop: the host reads step i-1's frames while step i is queued, so the
-        # GPU does not idle through the host's launch work; every step's frames reach the host and are read
-        if i > first_e2e[0]:
-            read_frames(i - 1)
-
-    def read_frames(i):
-        out_done[i & 1].synchronize()
-        host_sink[0] += float(out_host[i & 1][0, 0, 0, 0]) + float(out_host[i & 1][-1, -1, -1, -1])
-
-    first_e2e = [0]
-
     sampler = ClockSampler(local) if rank == 0 else None
-    # ---- arm 1: inputs resident in HBM ----
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier(world); torch.cuda.synchronize()
-    launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        step_resident(args.warmup + i)
-    ev1.record()
-    torch.cuda.synchronize(); barrier(world)
-    launches = _lib.launch_count() - launches0
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1), device, world)
-    ms_step = ms_total / args.steps
-    value = world * B / (ms_step / 1e3)
-    # ---- arm 2: end to end through the public API with host buffers ----
-    n_pre = min(args.warmup, 2)
-    for i in range(n_pre):
-        step_e2e(i)
-    if n_pre:
-        read_frames(n_pre - 1)
-    barrier(world); torch.cuda.synchronize()
-    first_e2e[0] = args.warmup
-    ev0.record()
-    for i in range(args.steps):
-        step_e2e(args.warmup + i)
-    read_frames(args.warmup + args.steps - 1)       # the last step's frames, inside the timed region
-    ev1.record()
-    torch.cuda.synchronize(); barrier(world)
-    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1), device, world) / args.steps
-    e2e_value = world * B / (ms_e2e / 1e3)
-    h2d = sum(z.numel() * 4 for z in lat_host[0])
-    d2h = out_host[0].numel() * 4
-    # ---- roofline of the dominant kernel: the point-network launches, CUDA events on their stream ----
-    roof = field_roofline(gen, args, lat_dev[0], md, device)
+    main = measure_model(args, args.model, world, rank, local, args.steps, args.warmup, sustained_s=0.0)
     clocks = sampler.stop() if sampler else None
+    extras = {}
+    if not args.quick:
+        other = "B" if args.model == "A" else "A"
+        short = max(5, min(args.steps, 10))
+        # the >= 3 s run of the headline workload, the other field (the curriculum BASELINE configs[2..4] name), the
+        # three precision modes, and the training-step shape
+        extras["sustained"] = measure_model(args, args.model, world, rank, local, args.steps, 3, sustained_s=3.0,
+                                            roofline=False)["sustained"]
+        extras["model_" + other.lower()] = measure_model(args, other, world, rank, local, short, 3)
+        modes = {}
+        for mode in ("exact", "fast", "guard"):
+            if mode == args.precision:
+                modes[mode] = main["value"]
+            else:
+                modes[mode] = measure_model(args, args.model, world, rank, local, 3 if mode == "exact" else short, 3,
+                                            precision=mode, roofline=False)["value"]
+        extras["modes"] = {"unit": "faces/s", **modes}
+        if world == 1:
+            try:
+                extras["train_step"] = measure_train_step(args, world, rank, local)
+            except Exception as e:   # never lose the headline line to the extra
+                extras["train_step"] = {"error": repr(e)[:300]}
     if rank != 0:
         return
     line = {
-        "metric": "rendered faces/sec at 128px x 24 samples/ray", "value": value, "unit": "faces/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "metric": "rendered faces/sec at 128px x 24 samples/ray", "value": main["value"], "unit": "faces/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate (tcgen05) + f32 refinement" if args.precision != "exact" else "f32",
         "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "faces/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h,
-                "pipeline": "double-buffered pinned output, D2H on a copy stream: step i-1's frames are read on the host while step i runs"},
-        "gpu_launches": int(launches), "roofline": roof,
+        "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "gpu_launches_per_step": main["gpu_launches_per_step"],
+        "cuda_graph": main["cuda_graph"], "roofline": main.get("roofline"),
     }
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         v, sample, cores = cpu_faces_per_sec(args.model, 1, 0, budget_s=40.0)
         line["cpu_baseline"] = {"value": v, "unit": "faces/s", "cores": cores, "kind": "port", "sample": sample}
     emit(line)
 
 
-def field_roofline(gen, args, latents, md, device):
+def field_roofline(gen, args, model, precision, latents, md, device):
     """Times the point-network launches of one step with CUDA events on the launching stream
-    (same sizes and inputs as inside the step: ray_setup -> field -> resample -> field)."""
+    (same sizes and inputs as inside the step: ray_setup -> field -> resample -> field).  The launches are
+    timed alone behind a GPU-side spin, i.e. in the burst-clock regime: `frac` is against the BURST bf16 peak of
+    MEASURED_PEAKS.json (`frac_of_sustained_peak` is given beside it)."""
     from fenerf_b200 import ops
     from fenerf_b200.generators import volumetric_rendering as vr
     peaks = {}
@@ -329,18 +461,18 @@ def field_roofline(gen, args, latents, md, device):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback (B200_PROFILING.md sustained ~1.4 PF)"
+    peak = peaks.get("bf16_tflops") or 1700.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone, ~1.5 ms launches)" if peaks else "fallback (B200_PROFILING.md ~1.7 PF burst)"
     B, S, R = latents[0].shape[0], md["num_steps"], md["img_size"]
     N = R * R
     with torch.no_grad():
-        if args.model == "A":
+        if model == "A":
             film = gen.siren.film_table(*gen.siren.mapping_network(latents[0]))
         else:
             fg, pg = gen.siren.geo_mapping_network(latents[0]); fa, pa = gen.siren.app_mapping_network(latents[1])
             film = gen.siren.film_table(fg, fa, pg, pa)
         rd = ops.make_render_desc(batch=B, img_size=R, num_steps=S, hierarchical=True, clamp_mode='relu', nerf_noise=0.0,
-                                  fov=md["fov"], precision=args.precision)
+                                  fov=md["fov"], precision=precision)
         x_lin, y_lin, z_lin = vr.ray_tables(R, S, md["ray_start"], md["ray_end"], device)
         c2w, _, _ = ops.camera_poses(B, 'gaussian', 0.3, 0.155, md["h_mean"], md["v_mean"], vr.DeviceRng(device), device)
         durations = []
@@ -362,17 +494,17 @@ def field_roofline(gen, args, latents, md, device):
                 durations += [e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])]
     durations.sort()
     ms = durations[len(durations) // 2] if len(durations) % 2 else 0.5 * (durations[len(durations) // 2 - 1] + durations[len(durations) // 2])
-    flops = B * N * S * FLOP_PER_POINT[args.model]
+    flops = B * N * S * FLOP_PER_POINT[model]
     achieved = flops / (ms * 1e-3) / 1e12
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%s" % (args.model, args.precision))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%s" % (model, precision))
     except Exception:
         pass
-    return {"bound": "tensor", "kernel": "siren point network (%s)" % args.precision, "achieved": achieved, "peak": peak,
+    return {"bound": "tensor", "kernel": "siren point network (%s, model %s)" % (precision, model), "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "ms_per_launch": ms,
             "flop_per_launch": flops, "peak_source": peak_src,
-            "frac_of_burst_peak": achieved / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None}
+            "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None}
 
 
 _RESULT_FD = None
@@ -406,6 +538,8 @@ def main():
     ap.add_argument("--model", default="A", choices=["A", "B"])
     ap.add_argument("--precision", default=os.environ.get("FENERF_B200_PRECISION", "guard"), choices=["guard", "fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as a captured CUDA graph")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (no sustained run / other model / modes / train step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -219,12 +219,14 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
                                  rd->noise_std, raw_c, guard, st)) return e;
     }
     if (rd->hierarchical) {
-        if (int e = resample(rd, C, raw_c, z_c, dirs, origins, noise_c, rng_u, z_f, points_f, (long long*)inds_dbg, st)) return e;
+        if (int e = resample(rd, C, raw_c, z_c, dirs, origins, noise_c, rng_u, z_f, points_f, (long long*)inds_dbg, st,
+                             /*sort_fine=*/1)) return e;
         if (int e = run_field(L, packed, points_f, dirs, film, rd->batch, ppb, rd->num_steps, rd->lock_view_dependence,
                               rd->precision, raw_f, st)) return e;
     }
-    return composite(rd, C, raw_c, z_c, rd->hierarchical ? raw_f : nullptr, rd->hierarchical ? z_f : nullptr, noise_f,
-                     pixels, depth, weights_sum, weights, nullptr, st);
+    // both sample lists are depth-sorted here: one thread per ray, accumulators in registers (composite.cu)
+    return composite_sorted(rd, C, raw_c, z_c, rd->hierarchical ? raw_f : nullptr, rd->hierarchical ? z_f : nullptr, noise_f,
+                            pixels, depth, weights_sum, weights, st);
 }
 
 // ---- backward ---------------------------------------------------------------

@@ -101,7 +101,10 @@ int ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_l
               float* origins, cudaStream_t st);
 int resample(const fenerf_render_desc* rd, int C, const float* raw, const float* z, const float* dirs,
              const float* origins, const float* noise, const float* u, float* z_fine, float* pts_fine,
-             long long* inds, cudaStream_t st);
+             long long* inds, cudaStream_t st, int sort_fine = 0);
+int composite_sorted(const fenerf_render_desc* rd, int C, const float* raw_c, const float* z_c, const float* raw_f,
+                     const float* z_f, const float* noise, float* pixels, float* depth, float* wsum, float* weights,
+                     cudaStream_t st);
 int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const float* z_c, const float* raw_f,
               const float* z_f, const float* noise, float* pixels, float* depth, float* wsum, float* weights,
               int32_t* sort_idx, cudaStream_t st);

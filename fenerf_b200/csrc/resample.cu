@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 resample_kernel(long long n_rays, long long rays_per_batch, int S, int C, int clamp_mode, float noise_std,
                 const float* __restrict__ raw, const float* __restrict__ z_vals, const float* __restrict__ dirs,
                 const float* __restrict__ origins, const float* __restrict__ noise, const float* __restrict__ u,
-                float* __restrict__ z_fine, float* __restrict__ pts_fine, long long* __restrict__ inds) {
+                float* __restrict__ z_fine, float* __restrict__ pts_fine, long long* __restrict__ inds, int sort_fine) {
     __shared__ float s_z[kWarpsPerBlock][kMaxS];
     __shared__ float s_t[kWarpsPerBlock][kMaxS];    // 1 - alpha + 1e-10
     __shared__ float s_a[kWarpsPerBlock][kMaxS];    // alpha
@@ -101,13 +101,32 @@ resample_kernel(long long n_rays, long long rays_per_batch, int S, int C, int cl
             float denom = __fsub_rn(ca, cb);
             if (denom < 1e-5f) denom = 1.f;
             float zf = __fadd_rn(bb, __fmul_rn(__fdiv_rn(__fsub_rn(uu, cb), denom), __fsub_rn(ba, bb)));
+            if (inds) inds[base + k] = lo;
+            if (sort_fine) { t[k] = zf; continue; }      // t[] is free by now: holds the unsorted fine depths
             z_fine[base + k] = zf;
             pts_fine[(base + k) * 3 + 0] = __fadd_rn(o0, __fmul_rn(d0, zf));
             pts_fine[(base + k) * 3 + 1] = __fadd_rn(o1, __fmul_rn(d1, zf));
             pts_fine[(base + k) * 3 + 2] = __fadd_rn(o2, __fmul_rn(d2, zf));
-            if (inds) inds[base + k] = lo;
         }
         __syncwarp();
+        if (sort_fine) {
+            // the render path wants the fine samples in depth order (the merge with the coarse list is then a
+            // two-pointer walk, composite.cu); the order of a ray's fine samples is otherwise immaterial: the
+            // reference sorts them itself right after (generators.py:85-89).  Stable rank sort, ties keep draw order.
+            for (int k = lane; k < S; k += 32) {
+                const float zk = t[k];
+                int r = 0;
+                for (int j = 0; j < S; ++j) {
+                    const float zj = t[j];
+                    r += (zj < zk) || (zj == zk && j < k);
+                }
+                z_fine[base + r] = zk;
+                pts_fine[(base + r) * 3 + 0] = __fadd_rn(o0, __fmul_rn(d0, zk));
+                pts_fine[(base + r) * 3 + 1] = __fadd_rn(o1, __fmul_rn(d1, zk));
+                pts_fine[(base + r) * 3 + 2] = __fadd_rn(o2, __fmul_rn(d2, zk));
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -115,7 +134,7 @@ resample_kernel(long long n_rays, long long rays_per_batch, int S, int C, int cl
 
 int resample(const fenerf_render_desc* rd, int C, const float* raw, const float* z, const float* dirs,
              const float* origins, const float* noise, const float* u, float* z_fine, float* pts_fine,
-             long long* inds, cudaStream_t st) {
+             long long* inds, cudaStream_t st, int sort_fine) {
     FN_REQUIRE(rd->num_steps >= 3 && rd->num_steps <= kMaxS, "num_steps %d outside [3, %d] for resampling",
                rd->num_steps, kMaxS);
     long long rpb = (long long)rd->img_h * rd->img_w;
@@ -125,7 +144,7 @@ int resample(const fenerf_render_desc* rd, int C, const float* raw, const float*
     int blocks = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
     if (blocks < 1) blocks = 1;
     resample_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(n_rays, rpb, rd->num_steps, C, rd->clamp_mode, rd->noise_std,
-                                                            raw, z, dirs, origins, noise, u, z_fine, pts_fine, inds);
+                                                            raw, z, dirs, origins, noise, u, z_fine, pts_fine, inds, sort_fine);
     FN_LAUNCH_OK("resample_kernel");
     return 0;
 }

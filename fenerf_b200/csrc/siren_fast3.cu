@@ -368,6 +368,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         };
         float next_pos[3], next_dir[3];      // fetched during the previous tile's last stage (off the tile-start path)
         bool have_next = false;
+        float sig_keep = 0.f;                // density of this thread's point: held from the trunk head to the rgb head so
+                                             // that [.., r, g, b, sigma] leaves in 16-byte (C = 4) / 8-byte stores
         for (long long pair = blockIdx.x; pair * 2 + t < a.n_tiles; pair += gridDim.x, ++tl) {
             const long long tile = pair * 2 + t;
             const long long b = tile / a.tiles_per_batch;
@@ -514,25 +516,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                         if (o < L.label_dim) orow[o] = v0;
                                         if (o + 1 < L.label_dim) orow[o + 1] = v1;
                                     }
-                                    if (o == L.label_dim) orow[C - 1] = __uint_as_float(r[o]) + __ldg(sigma_w + FN_H);
-                                    if (o + 1 == L.label_dim) orow[C - 1] = __uint_as_float(r[o + 1]) + __ldg(sigma_w + FN_H);
+                                    if (o == L.label_dim) sig_keep = __uint_as_float(r[o]) + __ldg(sigma_w + FN_H);
+                                    if (o + 1 == L.label_dim) sig_keep = __uint_as_float(r[o + 1]) + __ldg(sigma_w + FN_H);
                                 }
+                                if (a.sigma_only) orow[C - 1] = sig_keep;
                             }
                         } else {
                             uint32_t r[8];
                             tc_ld8(t_lane, r);
                             tc_wait_ld();
-                            if (valid) a.out[flat * C + (C - 1)] = __uint_as_float(r[0]) + __ldg(sigma_w + FN_H);
+                            sig_keep = __uint_as_float(r[0]) + __ldg(sigma_w + FN_H);
+                            if (valid && a.sigma_only) a.out[flat * C + (C - 1)] = sig_keep;
                         }
                     } else {
                         uint32_t r[8];
                         tc_ld8(t_lane, r);
                         tc_wait_ld();
                         if (valid) {
+                            float c3[3];
 #pragma unroll
                             for (int o = 0; o < 3; ++o) {
                                 const float x = __uint_as_float(r[o]) + __ldg(rgb_w + 3 * FN_H + o);
-                                a.out[flat * C + L.label_dim + o] = __fdividef(1.f, 1.f + __expf(-x));
+                                c3[o] = __fdividef(1.f, 1.f + __expf(-x));
+                            }
+                            // [r, g, b, sigma] is the tail of the point's row: 16 bytes at once when the row is 16 bytes
+                            // (C = 4), two 8-byte stores when C is even, scalars otherwise
+                            float* tail = a.out + flat * C + L.label_dim;
+                            const uintptr_t ob = reinterpret_cast<uintptr_t>(a.out);
+                            if (C == 4 && (ob & 15) == 0) {
+                                *reinterpret_cast<float4*>(tail) = make_float4(c3[0], c3[1], c3[2], sig_keep);
+                            } else if ((C & 1) == 0 && (ob & 7) == 0) {
+                                *reinterpret_cast<float2*>(tail) = make_float2(c3[0], c3[1]);
+                                *reinterpret_cast<float2*>(tail + 2) = make_float2(c3[2], sig_keep);
+                            } else {
+                                tail[0] = c3[0]; tail[1] = c3[1]; tail[2] = c3[2]; tail[3] = sig_keep;
                             }
                         }
                     }

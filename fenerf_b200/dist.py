@@ -47,9 +47,9 @@ def gather_frames(local_frames, group=None):
 
 
 class FrameGatherer:
-    """Preallocated equal-shard gather for the steady-state loop (bench / training): the render
-    writes into ``self.local`` -- a view of this rank's slice of the global frame buffer -- and
-    ``gather()`` issues the collective in place."""
+    """Preallocated equal-shard gather for the steady-state loop (bench / training): one
+    ``all_gather_into_tensor`` whose input is the render's own output buffer and whose output is the
+    preallocated global frame buffer."""
 
     def __init__(self, b_local, channels, img_size, device, group=None):
         self.group = group
@@ -59,11 +59,13 @@ class FrameGatherer:
         self.local = self.buffer[self.rank * b_local:(self.rank + 1) * b_local]
 
     def gather(self, frames=None):
-        if frames is not None and frames.data_ptr() != self.local.data_ptr():
-            self.local.copy_(frames)
+        """`frames` = this rank's (b_local, C, R, R) render output (any buffer: the collective reads it in place,
+        no staging copy), or None when the render wrote into ``self.local``."""
+        src = self.local if frames is None else frames
         if self.world > 1:
-            dist.all_gather_into_tensor(self.buffer, self.local, group=self.group)
-        return self.buffer
+            dist.all_gather_into_tensor(self.buffer, src.contiguous(), group=self.group)
+            return self.buffer
+        return src
 
 
 def render_sharded(generator, latents, metadata, group=None):

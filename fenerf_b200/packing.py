@@ -26,7 +26,10 @@ class PackedField:
         """Orders the caller's current stream after the pack kernels when it is a different stream."""
         cur = torch.cuda.current_stream(self.device)
         if self.event is not None and cur.cuda_stream != self.stream:
-            cur.wait_event(self.event)
+            if self.event.query():           # long finished (the steady state; also keeps graph capture clean)
+                self.event = None
+            else:
+                cur.wait_event(self.event)
 
 
 def field_desc(spec) -> "_lib.FieldDesc":
