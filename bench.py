@@ -361,7 +361,7 @@ def measure_train_step(args, world, rank, local):
     gen.train()
     R, S, BATCH, SPLIT = 64, 24, 32, 4
     md = dict(metadata(R), precision=args.precision)
-    opt = torch.optim.Adam(gen.parameters(), lr=6e-5, betas=(0, 0.9))
+    opt = torch.optim.Adam(gen.parameters(), lr=6e-5, betas=(0.0, 0.9))
     scaler = torch.amp.GradScaler("cuda")
     w = torch.randn((BATCH // SPLIT, gen.output_dim - 1, R, R), device=device) / (R * R)
 

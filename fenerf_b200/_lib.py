@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfenerf_b200.so")
+LIB_PATH = os.environ.get("FENERF_B200_LIB") or os.path.join(_HERE, "libfenerf_b200.so")   # env: experiment builds only
 
 MAX_TRUNK, MAX_COLOR, MAX_LABEL, HIDDEN = 8, 4, 32, 256
 

@@ -341,6 +341,11 @@ class RenderFunction(torch.autograd.Function):
             d_raw_c = torch.empty_like(st['raw_c'])
             d_raw_f = torch.empty_like(st['raw_f']) if hier else None
             noise = call['rng_noise_f'] if rd.noise_std != 0.0 else None
+            if call.get('grad_rays') is not None:
+                # gradient only through the chosen rays: the others were rendered under no_grad in the reference
+                mask = torch.zeros(n, dtype=torch.bool, device=dev)
+                mask[call['grad_rays']] = True
+                d_pixels = d_pixels * mask.reshape(1, 1, rd.img_h, rd.img_w)
             _lib.check(lib.fenerf_composite_backward(
                 C.byref(rd), c, st['raw_c'].data_ptr(), st['z_c'].data_ptr(), _ptr(st['raw_f']) if hier else 0,
                 _ptr(st['z_f']) if hier else 0, _ptr(noise), d_pixels.data_ptr(), d_raw_c.data_ptr(), _ptr(d_raw_f),
@@ -352,11 +357,20 @@ class RenderFunction(torch.autograd.Function):
             inv_scale = (1.0 / scale).float().reshape(1)
             fb = _FieldBackward(module, film, scale, inv_scale, exact=(rd.precision == _lib.PRECISION['exact']))
             lock = bool(rd.lock_view_dependence)
+            rays = call.get('grad_rays')
+            dirs = st['dirs']
+
+            def pick(t, last):
+                # (B, n, s, last) -> (B, n' * s, last): every ray, or only the rays that carry a gradient (part_forward)
+                if rays is not None:
+                    t = t.index_select(1, rays)
+                return t.reshape(B, -1, last)
+
+            if rays is not None:
+                dirs = dirs.index_select(1, rays).contiguous()
             if hier:
-                fb.add_points(st['points_f'].reshape(B, n * s, 3), st['dirs'], s, lock, st['raw_f'].reshape(B, n * s, c),
-                              d_raw_f.reshape(B, n * s, c))
-            fb.add_points(st['points_c'].reshape(B, n * s, 3), st['dirs'], s, lock, st['raw_c'].reshape(B, n * s, c),
-                          d_raw_c.reshape(B, n * s, c))
+                fb.add_points(pick(st['points_f'], 3), dirs, s, lock, pick(st['raw_f'], c), pick(d_raw_f, c))
+            fb.add_points(pick(st['points_c'], 3), dirs, s, lock, pick(st['raw_c'], c), pick(d_raw_c, c))
             d_film, grads = fb.finish()
         out = [d_film if ctx.needs_input_grad[0] else None, None]
         for i, pid in enumerate(ctx.param_ids):
@@ -367,10 +381,12 @@ class RenderFunction(torch.autograd.Function):
         return tuple(out)
 
 
-def render_with_grad(module, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb, rng_noise_c, rng_u, rng_noise_f):
-    """Differentiable render: (B, C-1, R, R) pixels with autograd edges to `film` and the field parameters."""
+def render_with_grad(module, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb, rng_noise_c, rng_u, rng_noise_f,
+                     grad_rays=None):
+    """Differentiable render: (B, C-1, R, R) pixels with autograd edges to `film` and the field parameters.
+    `grad_rays`: optional int64 ray indices -- only these rays carry the gradient (part_forward)."""
     fw = FieldWeights(module)
     params = fw.parameters()
     call = dict(module=module, rd=rd, x_lin=x_lin, y_lin=y_lin, z_lin=z_lin, cam2world=cam2world, rng_perturb=rng_perturb,
-                rng_noise_c=rng_noise_c, rng_u=rng_u, rng_noise_f=rng_noise_f, params=params)
+                rng_noise_c=rng_noise_c, rng_u=rng_u, rng_noise_f=rng_noise_f, params=params, grad_rays=grad_rays)
     return RenderFunction.apply(film, call, *params)

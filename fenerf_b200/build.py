@@ -21,6 +21,11 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-DFENERF_BUILDING_LIB",
 ]
+# experiment builds (tools/ab_field.py): FENERF_NVCC_DEFINES="-DFOO=1 ..." + FENERF_B200_LIB=<output .so>
+NVCC_FLAGS += os.environ.get("FENERF_NVCC_DEFINES", "").split()
+if os.environ.get("FENERF_B200_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["FENERF_B200_LIB"])
+    OBJ_DIR = os.path.join(ROOT, "build", "obj_" + os.path.basename(LIB_PATH).replace(".so", ""))
 
 
 def _sources():

@@ -100,7 +100,11 @@ struct Fast3Args {
 };
 
 template <bool kTrace>
+#ifdef FENERF_AB_MAXNREG
+__global__ void __maxnreg__(FENERF_AB_MAXNREG) siren_fast3_kernel(const __grid_constant__ Fast3Args a) {
+#else
 __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_constant__ Fast3Args a) {
+#endif
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -543,7 +547,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             // (C = 4), two 8-byte stores when C is even, scalars otherwise
                             float* tail = a.out + flat * C + L.label_dim;
                             const uintptr_t ob = reinterpret_cast<uintptr_t>(a.out);
+#ifdef FENERF_AB_SCALAR_STORES
+                            if (false) {
+#else
                             if (C == 4 && (ob & 15) == 0) {
+#endif
                                 *reinterpret_cast<float4*>(tail) = make_float4(c3[0], c3[1], c3[2], sig_keep);
                             } else if ((C & 1) == 0 && (ob & 7) == 0) {
                                 *reinterpret_cast<float2*>(tail) = make_float2(c3[0], c3[1]);

@@ -25,7 +25,7 @@ class _RenderSkeleton:
     """The one render skeleton all reference methods share (generators.py:41-104 etc.)."""
 
     def _render(self, film, batch_size, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean,
-                v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs, staged):
+                v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs, staged, grad_points=None):
         device = torch.device(self.device)
         if device.type != 'cuda':
             raise RuntimeError("fenerf_b200 renders on CUDA only; move the generator to a B200 (got %s)" % device)
@@ -44,12 +44,32 @@ class _RenderSkeleton:
                                                      device)
             x_lin, y_lin, z_lin = ops.ray_tables(img_size, num_steps, ray_start, ray_end, device)
             rng_noise_c = rng_u = None
-            if hierarchical_sample:
+            grad_rays = None
+            if grad_points is None:
+                if hierarchical_sample:
+                    clamp_mode, noise_std = kwargs['clamp_mode'], kwargs['nerf_noise']
+                    rng_noise_c = rng.randn(batch_size, n_rays, num_steps, 1)         # draw #4
+                    rng_u = rng.rand(batch_size * n_rays, num_steps)                  # draw #5
                 clamp_mode, noise_std = kwargs['clamp_mode'], kwargs['nerf_noise']
-                rng_noise_c = rng.randn(batch_size, n_rays, num_steps, 1)         # draw #4
-                rng_u = rng.rand(batch_size * n_rays, num_steps)                  # draw #5
-            clamp_mode, noise_std = kwargs['clamp_mode'], kwargs['nerf_noise']
-            rng_noise_f = rng.randn(batch_size, n_rays, n_samples, 1)             # draw #6
+                rng_noise_f = rng.randn(batch_size, n_rays, n_samples, 1)             # draw #6
+            else:
+                # part_forward (generators.py:858-910): a random subset of `grad_points` rays carries the gradient.  The
+                # reference renders the two subsets one after the other (point_forward twice), so its draws come per
+                # subset; they are scattered back to ray order here and ALL rays go through one fused render.
+                clamp_mode, noise_std = kwargs['clamp_mode'], kwargs['nerf_noise']
+                perm = rng.randperm(n_rays)
+                grad_rays = perm[:grad_points]
+                if hierarchical_sample:
+                    rng_noise_c = torch.empty((batch_size, n_rays, num_steps, 1), device=device)
+                    rng_u = torch.empty((batch_size, n_rays, num_steps), device=device)
+                rng_noise_f = torch.empty((batch_size, n_rays, n_samples, 1), device=device)
+                for idx in (grad_rays, perm[grad_points:]):
+                    if hierarchical_sample:
+                        rng_noise_c[:, idx] = rng.randn(batch_size, idx.numel(), num_steps, 1)
+                        rng_u[:, idx] = rng.rand(batch_size * idx.numel(), num_steps).reshape(batch_size, idx.numel(), num_steps)
+                    rng_noise_f[:, idx] = rng.randn(batch_size, idx.numel(), n_samples, 1)
+                if hierarchical_sample:
+                    rng_u = rng_u.reshape(batch_size * n_rays, num_steps)
             rd = ops.make_render_desc(
                 batch=batch_size, img_size=img_size, num_steps=num_steps, hierarchical=hierarchical_sample,
                 clamp_mode=clamp_mode, nerf_noise=noise_std, fov=fov, last_back=kwargs.get('last_back', False),
@@ -73,7 +93,7 @@ class _RenderSkeleton:
             # the differentiable call (G step, inversion): same kernels forward, backward in fenerf_b200/backward.py
             from .. import backward
             pixels = backward.render_with_grad(self.siren, rd, film, x_lin, y_lin, z_lin, cam2world,
-                                               rng_perturb.contiguous(), rng_noise_c, rng_u, rng_noise_f)
+                                               rng_perturb.contiguous(), rng_noise_c, rng_u, rng_noise_f, grad_rays=grad_rays)
             depth = wsum = weights = None
         return pixels, depth, wsum, weights, pitch, yaw
 
@@ -286,7 +306,13 @@ class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
 
     def part_forward(self, z_geo, z_app, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean,
                      v_mean, hierarchical_sample, sample_dist=None, lock_view_dependence=False, **kwargs):
+        """Ray-subset training (generators.py:858-910): every ray is rendered, `grad_points` randomly chosen ones carry
+        the gradient.  One fused render for all rays; the backward visits only the chosen rays' samples."""
         grad_points = kwargs.get('grad_points', img_size * img_size)
         assert img_size * img_size > grad_points
-        raise NotImplementedError("grad_points ray-subset training (generators.py:858-910) is not enabled by any "
-                                  "named curriculum and is not built (SURVEY.md section 2a)")
+        batch_size = z_app.shape[0]
+        film = self.siren.film_table(*self._map(z_geo, z_app))
+        pixels, _, _, _, pitch, yaw = self._render(
+            film, batch_size, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean,
+            hierarchical_sample, sample_dist, lock_view_dependence, kwargs, staged=False, grad_points=grad_points)
+        return pixels, torch.cat([pitch, yaw], -1)

@@ -32,6 +32,9 @@ class DeviceRng:
     def coin(self):
         return random.random()
 
+    def randperm(self, n):
+        return torch.randperm(n, device=self.device)
+
 
 class ReplayRng:
     """Replays draws recorded from an oracle run (tests): a list of (kind, tensor)."""
@@ -62,6 +65,12 @@ class ReplayRng:
         self.pos += 1
         assert k == "coin"
         return float(t)
+
+    def randperm(self, n):
+        k, t = self.draws[self.pos]
+        self.pos += 1
+        assert k == "randperm" and t.numel() == n
+        return t.to(self.device)
 
 
 # --------------------------------------------------------------------------------------------

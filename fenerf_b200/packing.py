@@ -24,8 +24,10 @@ class PackedField:
 
     def wait_ready(self):
         """Orders the caller's current stream after the pack kernels when it is a different stream."""
+        if self.event is None or torch.cuda.is_current_stream_capturing():
+            return      # (graph capture follows a warm-up + device synchronize, fenerf_b200/graphs.py: the pack is long done)
         cur = torch.cuda.current_stream(self.device)
-        if self.event is not None and cur.cuda_stream != self.stream:
+        if cur.cuda_stream != self.stream:
             if self.event.query():           # long finished (the steady state; also keeps graph capture clean)
                 self.event = None
             else:

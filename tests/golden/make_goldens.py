@@ -159,8 +159,61 @@ def frequency_grad_goldens():
         print("%-28s loss %.6f -> %s (%.1f KB)" % (name, loss.item(), os.path.basename(path), os.path.getsize(path) / 1024))
 
 
+class _RecordDraws:
+    """Records every torch.rand / randn / randperm made while the reference runs (part_forward draws per ray subset,
+    which the oracle does not restate): the GPU test replays them through ReplayRng."""
+
+    def __enter__(self):
+        self.log = []
+        self.saved = (torch.rand, torch.randn, torch.randperm)
+
+        def wrap(kind, fn):
+            def inner(*a, **k):
+                t = fn(*a, **k)
+                self.log.append((kind, t.clone()))
+                return t
+            return inner
+        torch.rand, torch.randn, torch.randperm = (wrap(k, f) for k, f in zip(("rand", "randn", "randperm"), self.saved))
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randn, torch.randperm = self.saved
+
+
+def part_forward_goldens():
+    """tests/golden/part_d_small.npz: ray-subset training (generators.py:858-910) -- frames, recorded draws and
+    gradients of DoubleImplicitGenerator3d.forward(..., grad_points=G)."""
+    ref_generators, ref_siren, _ = ref_shim.load()
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    case = _cases.CASE_BY_NAME["d_small"]
+    gen, _ = build_reference(case, ref_generators, ref_siren)
+    latents = tuple(z.clone().requires_grad_(True) for z in _cases.make_latents(case))
+    n_rays = case.cfg["img_size"] ** 2
+    kw = dict(case.cfg, grad_points=n_rays * 3 // 8)
+    torch.manual_seed(case.seed)
+    with _RecordDraws() as rec:
+        pixels, poses = gen(*latents, **kw)
+    loss = (pixels * _cases.loss_weights(pixels.shape)).sum()
+    loss.backward()
+    params = dict(gen.named_parameters())
+    out = {"loss": np.array(loss.item()), "pixels": pixels.detach().numpy(), "poses": poses.detach().numpy(),
+           "grad_points": np.array(kw["grad_points"]), "n_draws": np.array(len(rec.log))}
+    for i, (kind, t) in enumerate(rec.log):
+        out["draw%d_%s" % (i, kind)] = t.numpy()
+    for i, z in enumerate(latents):
+        out["g_latent%d" % i] = z.grad.numpy()
+    for k in GRAD_PARAMS[case.model]:
+        out["g_" + k] = params[k].grad.numpy()
+    path = os.path.join(out_dir, "part_d_small.npz")
+    np.savez_compressed(path, **out)
+    print("%-28s loss %.6f  %d draws -> %s (%.1f KB)" % ("part_d_small", loss.item(), len(rec.log), os.path.basename(path),
+                                                        os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
-    if sys.argv[1:2] == ["--grads"]:
+    if sys.argv[1:2] == ["--part"]:
+        part_forward_goldens()
+    elif sys.argv[1:2] == ["--grads"]:
         grad_goldens()
         frequency_grad_goldens()
     else:

@@ -389,6 +389,38 @@ def test_inversion_gradients_through_forward_with_frequencies(runs, name):
     assert all(p.grad is None for p in gen.parameters())
 
 
+def test_part_forward_ray_subset_training():
+    """generators.py:858-910 (`grad_points`): every ray rendered, a random 3/8 of them carry the gradient.  Frames,
+    poses and gradients against the reference's own part_forward, its draws (per ray subset) replayed."""
+    import os
+    gold = np.load(os.path.join(_cases.GOLDEN_DIR, "part_d_small.npz"))
+    case = _cases.CASE_BY_NAME["d_small"]
+    draws = []
+    for i in range(int(gold["n_draws"])):
+        key = next(k for k in gold.files if k.startswith("draw%d_" % i))
+        draws.append((key.split("_", 1)[1], torch.from_numpy(gold[key])))
+    gen = _cases.build_mirror(case, DEV)
+    latents = [_cuda(z).requires_grad_(True) for z in _cases.make_latents(case)]
+    pixels, poses = gen(*latents, **dict(case.cfg, grad_points=int(gold["grad_points"]), _rng=ReplayRng(draws, DEV)))
+    err = (pixels.detach().cpu() - torch.from_numpy(gold["pixels"])).abs().amax(1)
+    assert int((err > 1e-3).sum()) <= 2, "pixels beyond 1e-3: %d (max %g)" % (int((err > 1e-3).sum()), float(err.max()))
+    assert (poses.detach().cpu() - torch.from_numpy(gold["poses"])).abs().max() <= 1e-5
+    loss = (pixels * _cases.loss_weights(pixels.shape).to(DEV)).sum()
+    loss.backward()
+    got = {"g_latent%d" % i: z.grad for i, z in enumerate(latents)}
+    got.update({"g_" + k: p.grad for k, p in gen.named_parameters()})
+    worst = {}
+    for key in (k for k in gold.files if k.startswith("g_")):
+        want = torch.from_numpy(gold[key])
+        worst[key] = ((got[key].detach().cpu() - want).abs().max() / want.abs().max()).item()
+    bad = {k: "%.2e" % v for k, v in worst.items() if v > (0.3 if k[2:] in KINK_KEYS else 2e-2)}
+    assert not bad, "part_forward gradients: %s (all %s)" % (bad, {k: "%.1e" % v for k, v in worst.items()})
+    # and the no_grad flavour of the same call renders the same frames
+    with torch.no_grad():
+        px2, _ = gen(*[z.detach() for z in latents], **dict(case.cfg, grad_points=int(gold["grad_points"]), _rng=ReplayRng(draws, DEV)))
+    assert torch.equal(px2, pixels.detach())
+
+
 def test_backward_under_autocast_and_gradscaler():
     """The G step runs under torch.cuda.amp.autocast with a GradScaler (train_double_latent_semantic.py:405-446):
     the render node casts its inputs to fp32, returns fp32 pixels and survives a 2^16-scaled upstream gradient."""
