@@ -10,8 +10,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FENERF_B200_LIB") or os.path.join(_HERE, "libfenerf_b200.so")   # env: experiment builds only
 
-MAX_TRUNK, MAX_COLOR, MAX_LABEL, HIDDEN = 8, 4, 32, 256
+MAX_TRUNK, MAX_COLOR, MAX_LABEL, HIDDEN = 8, 8, 32, 256
 
+ABI_VERSION = 2
 PRECISION = {"exact": 0, "fast": 1, "guard": 2}
 CLAMP = {"relu": 0, "softplus": 1}
 FILL_MODE = {None: 0, "debug": 1, "weight": 2, "weight_debug": 3, "seg_padding_background": 4,
@@ -26,7 +27,7 @@ EXPORTS = (
     "fenerf_abi_version", "fenerf_launch_count", "fenerf_debug_trace", "fenerf_camera_poses",
     "fenerf_field_fingerprint", "fenerf_composite_backward", "fenerf_film_forward_stash", "fenerf_gate_backward",
     "fenerf_head_grads", "fenerf_extras_gather", "fenerf_grid_scatter_add", "fenerf_grid_unpack_grad",
-    "fenerf_workspace_layout",
+    "fenerf_workspace_layout", "fenerf_mask2color", "fenerf_frames_to_u8",
 )
 
 
@@ -101,6 +102,10 @@ def _declare(lib):
     lib.fenerf_grid_scatter_add.argtypes = [P(FieldDesc), vp, vp, i32, i64, vp, i32, vp]
     lib.fenerf_grid_unpack_grad.restype = C.c_int
     lib.fenerf_grid_unpack_grad.argtypes = [P(FieldDesc), vp, vp, vp, vp]
+    lib.fenerf_mask2color.restype = C.c_int
+    lib.fenerf_mask2color.argtypes = [vp, i32, i32, i64, vp, vp]
+    lib.fenerf_frames_to_u8.restype = C.c_int
+    lib.fenerf_frames_to_u8.argtypes = [vp, i32, i32, i32, i32, i64, vp, vp]
     lib.fenerf_last_error.restype = C.c_char_p
     lib.fenerf_last_error.argtypes = []
     lib.fenerf_abi_version.restype = i32
@@ -121,7 +126,7 @@ def lib():
                 "__graft_entry__.build(); the render path has no CPU / PyTorch fallback" % LIB_PATH)
         handle = C.CDLL(LIB_PATH)
         _declare(handle)
-        if handle.fenerf_abi_version() != 1:
+        if handle.fenerf_abi_version() != ABI_VERSION:
             raise RuntimeError("libfenerf_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -229,6 +229,19 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
                             pixels, depth, weights_sum, weights, st);
 }
 
+// ---- frame consumers --------------------------------------------------------
+int fenerf_mask2color(const float* masks, int32_t batch, int32_t n_labels, int64_t pixels_per_image, float* out, void* stream) {
+    FN_REQUIRE(masks && out && batch >= 1 && n_labels >= 1 && pixels_per_image >= 1, "bad argument");
+    return mask2color(masks, batch, n_labels, pixels_per_image, out, (cudaStream_t)stream);
+}
+
+int fenerf_frames_to_u8(const float* frames, int32_t batch, int32_t channels, int32_t first_channel, int32_t n_channels,
+                        int64_t pixels_per_image, uint8_t* out, void* stream) {
+    FN_REQUIRE(frames && out && batch >= 1 && n_channels >= 1 && first_channel >= 0 && first_channel + n_channels <= channels &&
+               pixels_per_image >= 1, "bad argument");
+    return frames_to_u8(frames, batch, channels, first_channel, n_channels, pixels_per_image, out, (cudaStream_t)stream);
+}
+
 // ---- backward ---------------------------------------------------------------
 int fenerf_composite_backward(const fenerf_render_desc* rd, int32_t out_dim, const float* raw_coarse, const float* z_coarse,
                               const float* raw_fine, const float* z_fine, const float* rng_noise, const float* d_pixels,

@@ -109,6 +109,9 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
               const float* z_f, const float* noise, float* pixels, float* depth, float* wsum, float* weights,
               int32_t* sort_idx, cudaStream_t st);
 
+// frames.cu
+int mask2color(const float* masks, int B, int K, long long HW, float* out, cudaStream_t st);
+int frames_to_u8(const float* frames, int B, int C, int c0, int nc, long long HW, unsigned char* out, cudaStream_t st);
 // backward.cu
 int composite_backward(const fenerf_render_desc* rd, int C, const float* raw_c, const float* z_c, const float* raw_f,
                        const float* z_f, const float* noise, const float* d_pixels, float* d_raw_c, float* d_raw_f,

@@ -30,7 +30,7 @@
 #include "../../include/fenerf_b200.h"
 
 #define FN_H 256            // hidden width
-#define FN_MAX_HIDDEN 11    // (8-1) trunk + 4 colour
+#define FN_MAX_HIDDEN 15    // (8-1) trunk + 8 colour
 #define FN_KCHUNK 64        // k elements per 128-byte swizzle row
 #define FN_IMG_BYTES (256 * FN_KCHUNK * 2)   // one [256][64] f16 image = 32 KB
 #define FN_SLOT_POS 0

@@ -48,10 +48,10 @@ constexpr uint32_t TILE_SMEM = 4 * CHUNK_BYTES;      // four activation chunks p
 constexpr uint32_t SMEM_RING = 2 * TILE_SMEM;
 constexpr uint32_t SMEM_BAR = SMEM_RING + RING * STAGE_BYTES;   // 229376
 constexpr uint32_t SMEM_TAB = SMEM_BAR + 256;                     // per-tile program: loads, then stages
-constexpr uint32_t SMEM_TOTAL = SMEM_TAB + 96 * 16 + 16 * 8;     // 231296
+constexpr uint32_t SMEM_TOTAL = SMEM_TAB + 96 * 16 + 24 * 8;     // 231360
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_LOADS = 96;
-constexpr int MAX_STAGES = 16;
+constexpr int MAX_STAGES = 24;
 
 enum : uint8_t { EPI_FILM = 0, EPI_HEAD_TRUNK = 1, EPI_HEAD_RGB = 2 };
 enum : uint8_t { X_NONE = 0, X_POS = 1, X_EXTRA = 2 };   // load reads the K-major input slots instead of an activation chunk

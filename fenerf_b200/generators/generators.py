@@ -205,6 +205,34 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
         return pixels, torch.cat([pitch, yaw], -1)
 
 
+class StyleGenerator3d(ImplicitGenerator3d):
+    """generators.py:914-1294: the single-latent generator that hands the latent to the point network itself
+    (``self.siren(points, z, ray_directions=...)``) -- no average-frequency table (``set_device`` draws nothing) and
+    no psi truncation in ``staged_forward`` (``psi`` is accepted and ignored, :1021-1088).  Everything else is the
+    ImplicitGenerator3d skeleton; ``staged_forward_with_frequencies`` / ``forward_with_frequencies`` are inherited."""
+
+    def set_device(self, device):
+        self.device = device
+        self.siren.device = device
+
+    def staged_forward(self, z, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean,
+                       psi=1, lock_view_dependence=False, max_batch_size=50000, depth_map=False, near_clip=0,
+                       far_clip=2, sample_dist=None, hierarchical_sample=False, **kwargs):
+        if 'img_feat_size' in kwargs:
+            img_size = kwargs['img_feat_size']
+        self._check_no_neural_renderer()
+        batch_size = z.shape[0]
+        with torch.no_grad():
+            frequencies, phase_shifts = self.siren.mapping_network(z)
+            pixels, depth, wsum, _, _, _ = self._render(
+                self._film(frequencies, phase_shifts), batch_size, img_size, fov, ray_start, ray_end, num_steps,
+                h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs,
+                staged=True)
+            depth_map = depth.reshape(batch_size, img_size, img_size).contiguous().cpu()
+            third = self._third_output(pixels, wsum, None, batch_size, img_size)
+        return pixels, depth_map, third
+
+
 class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
     def __init__(self, siren, z_geo_dim, z_app_dim, output_dim, softmax_label=False, **kwargs):
         super().__init__()

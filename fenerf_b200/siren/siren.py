@@ -16,6 +16,9 @@ Reference interfaces mirrored (file:line under /root/reference):
   UniformBoxWarp                              siren/siren.py:181-187
   sample_from_3dgrid                          siren/siren.py:314-330
   SPATIALSIRENBASELINE                        siren/siren.py:189-244
+  SPATIALSIRENBASELINESEMANTIC                siren/siren.py:674-744
+  SPATIALSIRENDISENTANGLE                     siren/siren.py:747-813
+  SPATIALSIRENSEMANTICDISENTANGLE             siren/siren.py:1085-1161
   SIRENBASELINESEMANTICDISENTANGLE            siren/siren.py:1163-1229
   TextureEmbeddingPiGAN128SEMANTICDISENTANGLE siren/siren.py:1451-1530
   ...256SEMANTICDISENTANGLE / ..._DIM_96      siren/siren.py:1533-1546
@@ -296,6 +299,37 @@ class SPATIALSIRENBASELINE(TALLSIREN):
                          grid_res=0, input_scale=float(self.gridwarper.scale_factor), out_dim=4, double_latent=False)
 
 
+class SPATIALSIRENBASELINESEMANTIC(TALLSIREN):
+    """SPATIALSIRENBASELINE plus a two-Linear semantic head with a fixed 19 labels (siren/siren.py:674-744):
+    output channels [labels (19), rgb (3), sigma (1)] whatever `output_dim` says."""
+
+    def __init__(self, input_dim=2, z_dim=100, hidden_dim=256, output_dim=1, device=None):
+        nn.Module.__init__(self)
+        self.device = device
+        self.input_dim = input_dim
+        self.z_dim = z_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+
+        widths = [3] + [hidden_dim] * 8
+        self.network = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        self.final_layer = nn.Linear(hidden_dim, 1)
+        self.label_layer_linear = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.Linear(hidden_dim, 19))
+        self.color_layer_sine = FiLMLayer(hidden_dim + 3, hidden_dim)
+        self.color_layer_linear = nn.Sequential(nn.Linear(hidden_dim, 3))
+        self.mapping_network = CustomMappingNetwork(z_dim, 256, (len(self.network) + 1) * hidden_dim * 2)
+
+        for part in (self.network, self.final_layer, self.label_layer_linear, self.color_layer_sine,
+                     self.color_layer_linear):
+            part.apply(frequency_init(25))
+        self.network[0].apply(first_layer_film_sine_init)
+        self.gridwarper = UniformBoxWarp(0.24)
+
+    def field_spec(self):
+        return FieldSpec(trunk_layers=len(self.network), color_layers=1, label_dim=19, grid_channels=0, grid_res=0,
+                         input_scale=float(self.gridwarper.scale_factor), out_dim=23, double_latent=False)
+
+
 class _DoubleLatentField(_FieldBase):
     """forward / FiLM-table plumbing shared by the double-latent (geometry, appearance) fields."""
 
@@ -347,6 +381,75 @@ class SIRENBASELINESEMANTICDISENTANGLE(_DoubleLatentField):
                      self.label_layer_linear):
             part.apply(frequency_init(25))
         self.network[0].apply(first_layer_film_sine_init)
+        self.gridwarper = UniformBoxWarp(0.24)
+
+    def field_spec(self):
+        return FieldSpec(trunk_layers=len(self.network), color_layers=len(self.color_layer_sine),
+                         label_dim=self.output_dim - 4, grid_channels=0, grid_res=0,
+                         input_scale=float(self.gridwarper.scale_factor), out_dim=self.output_dim, double_latent=True)
+
+
+class SPATIALSIRENDISENTANGLE(_DoubleLatentField):
+    """Geometry / appearance latents without a semantic head (siren/siren.py:747-813): 8 trunk FiLM layers on the
+    geometry code, 3 colour FiLM layers on the appearance code, output [rgb, sigma]."""
+
+    def __init__(self, input_dim=2, z_geo_dim=100, z_app_dim=100, hidden_dim=256, output_dim=1, device=None):
+        super().__init__()
+        self.device = device
+        self.input_dim = input_dim
+        self.z_geo_dim = z_geo_dim
+        self.z_app_dim = z_app_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+
+        widths = [3] + [hidden_dim] * 8
+        self.network = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        self.final_layer = nn.Linear(hidden_dim, 1)
+        cwidths = [hidden_dim + 3] + [hidden_dim] * 3
+        self.color_layer_sine = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(cwidths[:-1], cwidths[1:]))
+        self.color_layer_linear = nn.Sequential(nn.Linear(hidden_dim, 3))
+        self.geo_mapping_network = CustomMappingNetwork(z_geo_dim, 256, len(self.network) * hidden_dim * 2)
+        self.app_mapping_network = CustomMappingNetwork(z_app_dim, 256, len(self.color_layer_sine) * hidden_dim * 2)
+
+        for part in (self.network, self.final_layer, self.color_layer_sine, self.color_layer_linear):
+            part.apply(frequency_init(25))
+        self.network[0].apply(first_layer_film_sine_init)
+        self.gridwarper = UniformBoxWarp(0.24)
+
+    def field_spec(self):
+        return FieldSpec(trunk_layers=len(self.network), color_layers=len(self.color_layer_sine), label_dim=0,
+                         grid_channels=0, grid_res=0, input_scale=float(self.gridwarper.scale_factor), out_dim=4,
+                         double_latent=True)
+
+
+class SPATIALSIRENSEMANTICDISENTANGLE(_DoubleLatentField):
+    """The deep-appearance variant (siren/siren.py:1085-1161): 8 trunk + EIGHT colour FiLM layers, a two-Linear
+    semantic head; the first colour layer gets the U(+-1/fan_in) first-layer init as well (:1131)."""
+
+    def __init__(self, input_dim=2, z_geo_dim=100, z_app_dim=100, hidden_dim=256, output_dim=1, device=None):
+        super().__init__()
+        self.device = device
+        self.input_dim = input_dim
+        self.z_geo_dim = z_geo_dim
+        self.z_app_dim = z_app_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+
+        widths = [3] + [hidden_dim] * 8
+        self.network = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        self.final_layer = nn.Linear(hidden_dim, 1)
+        cwidths = [hidden_dim + 3] + [hidden_dim] * 8
+        self.color_layer_sine = nn.ModuleList(FiLMLayer(a, b) for a, b in zip(cwidths[:-1], cwidths[1:]))
+        self.color_layer_linear = nn.Sequential(nn.Linear(hidden_dim, 3))
+        self.geo_mapping_network = CustomMappingNetwork(z_geo_dim, 256, len(self.network) * hidden_dim * 2)
+        self.app_mapping_network = CustomMappingNetwork(z_app_dim, 256, len(self.color_layer_sine) * hidden_dim * 2)
+        self.label_layer_linear = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.Linear(hidden_dim, self.output_dim - 4))
+
+        for part in (self.network, self.final_layer, self.color_layer_sine, self.color_layer_linear,
+                     self.label_layer_linear):
+            part.apply(frequency_init(25))
+        self.network[0].apply(first_layer_film_sine_init)
+        self.color_layer_sine[0].apply(first_layer_film_sine_init)
         self.gridwarper = UniformBoxWarp(0.24)
 
     def field_spec(self):

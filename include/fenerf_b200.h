@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FENERF_ABI_VERSION 1
+#define FENERF_ABI_VERSION 2   /* 2: FENERF_MAX_COLOR 4 -> 8 (fenerf_field_params grew), backward entry points */
 
 /* error codes */
 #define FENERF_OK            0
@@ -53,13 +53,13 @@ extern "C" {
  *                                trunk 8, color 3, label 18, grid 32 x 96^3, scale 2/0.24, out 22.
  * The hidden width is fixed at 256.                                                            */
 #define FENERF_MAX_TRUNK 8
-#define FENERF_MAX_COLOR 4
+#define FENERF_MAX_COLOR 8
 #define FENERF_MAX_LABEL 32
 #define FENERF_HIDDEN 256
 
 typedef struct fenerf_field_desc {
     int32_t trunk_layers;   /* 2..8 */
-    int32_t color_layers;   /* 1..4 */
+    int32_t color_layers;   /* 1..8 */
     int32_t label_dim;      /* 0..32 */
     int32_t grid_channels;  /* 0 or 32 */
     int32_t grid_res;       /* cubic grid side (D = H = W), 0 if no grid */
@@ -257,6 +257,16 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
                           float* pixels, float* depth, float* weights_sum, float* weights,
                           int64_t* inds_dbg, void* workspace, size_t workspace_bytes,
                           void* stream);
+
+/* ---- frame consumers ---------------------------------------------------------------------------------
+ * mask2color (train_double_latent_semantic.py:36-55, 66-72): masks (B, K, H, W) -> argmax over K -> the reference's
+ * 19-entry colour table -> out (B, 3, H, W) float in 0..255 (classes >= 19 stay black, as in the reference). */
+int fenerf_mask2color(const float* masks, int32_t batch, int32_t n_labels, int64_t pixels_per_image, float* out, void* stream);
+/* frames (B, C, H, W) in [-1, 1] -> out (B, H, W, n_channels) uint8 of channels [first_channel, first_channel + n_channels):
+ * torchvision.utils.save_image(img, normalize=True, range=(-1, 1)) rounding (fid_evaluation.py:146-151) -- the JPEG
+ * encoder's input, a quarter of the bytes to move to the host. */
+int fenerf_frames_to_u8(const float* frames, int32_t batch, int32_t channels, int32_t first_channel, int32_t n_channels,
+                        int64_t pixels_per_image, uint8_t* out, void* stream);
 
 /* ---- backward of the render ---------------------------------------------------------------------
  * What the reference differentiates (train_double_latent_semantic.py:405-446 G step,

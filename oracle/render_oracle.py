@@ -332,3 +332,30 @@ def film_from_latents(field, latents):
             p = torch.cat([p_geo, p_app], -1)
         b = f.shape[0]
         return torch.stack([f.reshape(b, -1, 256), p.reshape(b, -1, 256)], dim=2).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# frame consumers        train_double_latent_semantic.py:36-55, 66-72; fid_evaluation.py:146-151
+# --------------------------------------------------------------------------------------------
+COLOR_MAP = {0: [0, 0, 0], 1: [204, 0, 0], 2: [76, 153, 0], 3: [204, 204, 0], 4: [51, 51, 255], 5: [204, 0, 204],
+             6: [0, 255, 255], 7: [255, 204, 204], 8: [102, 51, 0], 9: [255, 0, 0], 10: [102, 204, 0], 11: [255, 255, 0],
+             12: [0, 0, 153], 13: [0, 0, 204], 14: [255, 51, 153], 15: [0, 204, 204], 16: [0, 51, 0], 17: [255, 153, 51],
+             18: [0, 204, 0]}
+
+
+def mask2color(masks):
+    """train_double_latent_semantic.py:66-72."""
+    masks = torch.argmax(masks, dim=1).float()
+    sample_mask = torch.zeros((masks.shape[0], masks.shape[1], masks.shape[2], 3), dtype=torch.float)
+    for key in COLOR_MAP:
+        sample_mask[masks == key] = torch.tensor(COLOR_MAP[key], dtype=torch.float)
+    return sample_mask.permute(0, 3, 1, 2)
+
+
+def save_image_bytes(img):
+    """The uint8 HWC array torchvision.utils.save_image(img, normalize=True, range=(-1, 1)) hands to PIL
+    (fid_evaluation.py:149; torchvision 0.x utils.py:84-90 norm_ip: clamp to the range, sub low, div max(high - low, 1e-5);
+    then save_image's mul(255).add_(0.5).clamp_(0, 255).to(uint8))."""
+    x = img.clone().float().clamp_(min=-1, max=1)
+    x = (x - (-1)) / max(1 - (-1), 1e-5)
+    return x.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8)

@@ -26,6 +26,13 @@ MODELS = {
     # D with 19 label channels: the only width at which the reference's 'debug' / 'weight_debug' fill modes run at
     # all -- they assign a hard-coded 22-vector to the (C-1)-channel pixels (volumetric_rendering.py:54, 66)
     "E": ("DoubleImplicitGenerator3d", "SIRENBASELINESEMANTICDISENTANGLE", 2, 23),
+    # the third wrapper type of generators.py (:914-1294): no avg-frequency table, no psi truncation
+    "S": ("StyleGenerator3d", "TALLSIREN", 1, 4),
+    # three more of siren.py's variants through the same kernels (FieldSpec table): single latent + semantic head,
+    # double latent without one, and the 8 + 8 layer deep-appearance network
+    "F": ("ImplicitGenerator3d", "SPATIALSIRENBASELINESEMANTIC", 1, 23),
+    "G": ("DoubleImplicitGenerator3d", "SPATIALSIRENDISENTANGLE", 2, 4),
+    "H": ("DoubleImplicitGenerator3d", "SPATIALSIRENSEMANTICDISENTANGLE", 2, 22),
 }
 
 
@@ -110,6 +117,12 @@ CASES = [
                                               sample_dist='truncated_gaussian')),
     Case("a_cam_spherical", "A", 2, 50, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0,
                                              sample_dist='spherical_uniform')),
+    Case("s_small", "S", 2, 53, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("s_staged_weight", "S", 1, 54, _cfg(img_size=12, num_steps=9, h_stddev=0.0, v_stddev=0.0, nerf_noise=0.0,
+                                             fill_mode='weight'), method="staged_forward", psi=0.7),
+    Case("f_small", "F", 1, 55, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("g_small", "G", 2, 56, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
+    Case("h_small", "H", 1, 57, _cfg(img_size=12, num_steps=9, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
     # ---- the benchmarked shapes themselves (BASELINE.json configs[1] and the configs[4] shape), one face each ----
     Case("a_cfg2", "A", 1, 61, _cfg(img_size=128, num_steps=24, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
     Case("b_cfg2", "B", 1, 62, _cfg(img_size=128, num_steps=24, h_stddev=0.3, v_stddev=0.155, nerf_noise=0.0)),
@@ -169,6 +182,11 @@ def build_mirror(case, device="cpu"):
     gen.device = device
     gen.siren.device = device
     return gen
+
+
+def has_avg_frequencies(case):
+    """StyleGenerator3d has no average-frequency table: its staged_forward neither draws nor truncates."""
+    return MODELS[case.model][0] != "StyleGenerator3d"
 
 
 def avg_film_draws(case):

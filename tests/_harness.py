@@ -25,7 +25,7 @@ def oracle_run(case, gen=None, keep_stages=True):
     avg_draws = None
     with torch.no_grad():
         film = oracle.film_from_latents(gen.siren, latents)
-        if case.method == "staged_forward":
+        if case.method == "staged_forward" and _cases.has_avg_frequencies(case):
             # generate_avg_frequencies draws first, then psi-truncation towards the mean FiLM
             # parameters (generators.py:142-149, 554-564); equivalent in table form because
             # 15 (a + psi (f - a)) + 30 is evaluated from the truncated raw frequency

@@ -41,7 +41,7 @@ def state_digest(module):
 def build_reference(case, ref_generators, ref_siren):
     torch.manual_seed(0)
     gen = _cases.construct(ref_generators, ref_siren, case.model, case.cfg.get("softmax_label", False))
-    gen.set_device("cpu")
+    gen.set_device("cpu")      # (draws the avg-frequency latents for the Implicit / Double wrappers; nothing for Style)
     gen.eval()
     digest = state_digest(gen)
     _cases.apply_weight_edits(gen, case)

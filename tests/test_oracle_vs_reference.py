@@ -13,7 +13,7 @@ pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree
 
 @pytest.mark.parametrize("name", ["a_small", "a_small_noise", "a_nohier_softplus", "a_lockview_uniform", "b_small", "c_small", "d_small",
                                   "a_hier_softplus", "b_noise_b2", "a_cam_hybrid", "a_cam_hybrid2", "a_cam_truncgauss",
-                                  "a_cam_spherical"])
+                                  "a_cam_spherical", "s_small", "f_small", "g_small", "h_small"])
 def test_oracle_is_bit_exact_with_reference(name):
     import sys
     sys.path.insert(0, _cases.GOLDEN_DIR)
