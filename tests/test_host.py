@@ -18,7 +18,7 @@ ROOT = _cases.ROOT
 def _header_functions():
     text = open(os.path.join(ROOT, "include", "fenerf_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(fenerf_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(fenerf_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_symbol_the_header_declares():
