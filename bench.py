@@ -228,6 +228,10 @@ class StepRunner:
         self.lat_dev = [tuple(z.to(device) for z in zs) for zs in self.lat_host]
         self.gatherer = FrameGatherer(B, self.C_img, IMG, device)
         self.out_host = [torch.empty((world * B, self.C_img, IMG, IMG), dtype=torch.float32).pin_memory() for _ in range(2)]
+        # device-side staging, double-buffered: the render / gather output buffer is rewritten every step (it is the
+        # captured graph's static output), so the step's frames are moved aside (a ~2 us D2D copy) and the D2H runs from
+        # there on the copy stream -- the next step never waits for a D2H
+        self.stage = [torch.empty((world * B, self.C_img, IMG, IMG), dtype=torch.float32, device=device) for _ in range(2)]
         self.out_done = [torch.cuda.Event() for _ in range(2)]
         self.frames_ready = [torch.cuda.Event() for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=device)
@@ -249,9 +253,9 @@ class StepRunner:
 
     def step_e2e(self, i):
         k = i % len(self.lat_host)
-        if i > self.first_e2e:
-            # the frame buffer is reused every step: wait (on the GPU) until the previous D2H has read it
-            torch.cuda.current_stream().wait_event(self.out_done[(i - 1) & 1])
+        if i > self.first_e2e + 1:
+            # stage[i & 1] was last read by the D2H of step i-2: long finished, but keep the order explicit
+            torch.cuda.current_stream().wait_event(self.out_done[i & 1])
         if self.graph is not None:
             frames = self.graph(*self.lat_host[k])                 # H2D straight into the captured input buffers
             frames = frames[0]
@@ -260,10 +264,11 @@ class StepRunner:
             with torch.no_grad():
                 frames = self.gen(*zs, **self.md)[0]
         allf = self.gatherer.gather(frames)
+        self.stage[i & 1].copy_(allf)
         self.frames_ready[i & 1].record()
         self.copy_stream.wait_event(self.frames_ready[i & 1])
         with torch.cuda.stream(self.copy_stream):   # D2H on its own stream: the next step's kernels do not queue behind it
-            self.out_host[i & 1].copy_(allf, non_blocking=True)
+            self.out_host[i & 1].copy_(self.stage[i & 1], non_blocking=True)
             self.out_done[i & 1].record()
         # double-buffered serving loop: the host reads step i-1's frames while step i is queued; every step's
         # frames reach the host and are read inside the timed region
@@ -334,8 +339,9 @@ def measure_model(args, model, world, rank, local, steps, warmup, precision=None
            "ms_per_step": ms_step, "cuda_graph": r.graph is not None,
            "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "faces/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h,
-                   "pipeline": "pinned latents -> H2D -> render (one CUDA graph launch) -> frame all-gather -> D2H on a copy stream into "
-                               "double-buffered pinned memory; step i-1's frames are read on the host while step i runs"},
+                   "pipeline": "pinned latents -> H2D -> render (one CUDA graph launch) -> frame all-gather -> D2D into a double-buffered "
+                               "staging tensor -> D2H on a copy stream into double-buffered pinned memory; step i-1's frames are read on "
+                               "the host while step i runs"},
            "gpu_launches_per_step": lps, "gpu_launches": lps * steps}
     if sustained_s > 0:
         # a >= 3 s run: long enough to leave the boost clock / reach the power limit
