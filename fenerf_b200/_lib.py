@@ -27,7 +27,7 @@ EXPORTS = (
     "fenerf_abi_version", "fenerf_launch_count", "fenerf_debug_trace", "fenerf_camera_poses",
     "fenerf_field_fingerprint", "fenerf_composite_backward", "fenerf_film_forward_stash", "fenerf_gate_backward",
     "fenerf_head_grads", "fenerf_extras_gather", "fenerf_grid_scatter_add", "fenerf_grid_unpack_grad",
-    "fenerf_workspace_layout", "fenerf_mask2color", "fenerf_frames_to_u8",
+    "fenerf_workspace_layout", "fenerf_mask2color", "fenerf_frames_to_u8", "fenerf_mapping_film",
 )
 
 
@@ -53,6 +53,10 @@ class RenderDesc(C.Structure):
                 ("fill_mode", C.c_int32), ("fill_color", C.c_float), ("softmax_label", C.c_int32),
                 ("lock_view_dependence", C.c_int32), ("precision", C.c_int32),
                 ("noise_std", C.c_float), ("tan_half_fov", C.c_float), ("guard_tau", C.c_float)]
+
+
+class MappingParams(C.Structure):
+    _fields_ = [("weight", C.c_void_p * 5), ("bias", C.c_void_p * 5), ("z_dim", C.c_int32), ("hidden_dim", C.c_int32)]
 
 
 class WorkspaceOffsets(C.Structure):
@@ -102,6 +106,8 @@ def _declare(lib):
     lib.fenerf_grid_scatter_add.argtypes = [P(FieldDesc), vp, vp, i32, i64, vp, i32, vp]
     lib.fenerf_grid_unpack_grad.restype = C.c_int
     lib.fenerf_grid_unpack_grad.argtypes = [P(FieldDesc), vp, vp, vp, vp]
+    lib.fenerf_mapping_film.restype = C.c_int
+    lib.fenerf_mapping_film.argtypes = [P(MappingParams), vp, i32, i32, i32, i32, vp, vp, C.c_float, vp, vp, vp]
     lib.fenerf_mask2color.restype = C.c_int
     lib.fenerf_mask2color.argtypes = [vp, i32, i32, i64, vp, vp]
     lib.fenerf_frames_to_u8.restype = C.c_int

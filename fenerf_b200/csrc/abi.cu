@@ -229,6 +229,18 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
                             pixels, depth, weights_sum, weights, st);
 }
 
+int fenerf_mapping_film(const fenerf_mapping_params* net, const float* z, int32_t batch, int32_t n_layers, int32_t first_layer,
+                        int32_t n_film_total, const float* avg_frequencies, const float* avg_phase_shifts, float psi,
+                        float* h_scratch, float* film, void* stream) {
+    FN_REQUIRE(net && z && h_scratch && film && batch >= 1 && n_layers >= 1 && first_layer >= 0 &&
+               first_layer + n_layers <= n_film_total, "bad argument");
+    FN_REQUIRE((avg_frequencies == nullptr) == (avg_phase_shifts == nullptr), "give both averages or neither");
+    for (int i = 0; i < 5; ++i) FN_REQUIRE(net->weight[i] && net->bias[i], "mapping layer %d missing", i);
+    FN_REQUIRE(net->hidden_dim == 256, "mapping network hidden width must be 256");
+    return mapping_film(net->weight, net->bias, z, batch, net->z_dim, n_layers, first_layer, n_film_total, avg_frequencies,
+                        avg_phase_shifts, psi, h_scratch, film, (cudaStream_t)stream);
+}
+
 // ---- frame consumers --------------------------------------------------------
 int fenerf_mask2color(const float* masks, int32_t batch, int32_t n_labels, int64_t pixels_per_image, float* out, void* stream) {
     FN_REQUIRE(masks && out && batch >= 1 && n_labels >= 1 && pixels_per_image >= 1, "bad argument");

@@ -109,6 +109,10 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
               const float* z_f, const float* noise, float* pixels, float* depth, float* wsum, float* weights,
               int32_t* sort_idx, cudaStream_t st);
 
+// mapping.cu
+int mapping_film(const float* const* w, const float* const* b, const float* z, int B, int z_dim, int n_layers, int layer0,
+                 int n_film_total, const float* avg_f, const float* avg_p, float psi, float* h_scratch, float* film,
+                 cudaStream_t st);
 // frames.cu
 int mask2color(const float* masks, int B, int K, long long HW, float* out, cudaStream_t st);
 int frames_to_u8(const float* frames, int B, int C, int c0, int nc, long long HW, unsigned char* out, cudaStream_t st);

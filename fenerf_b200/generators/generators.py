@@ -148,9 +148,8 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
         if 'img_feat_size' in kwargs:
             img_size = kwargs['img_feat_size']
         self._check_no_neural_renderer()
-        frequencies, phase_shifts = self.siren.mapping_network(z)
         pixels, _, _, _, pitch, yaw = self._render(
-            self._film(frequencies, phase_shifts), z.shape[0], img_size, fov, ray_start, ray_end, num_steps, h_stddev,
+            self.siren.film_from_latents(z), z.shape[0], img_size, fov, ray_start, ray_end, num_steps, h_stddev,
             v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs, staged=False)
         return pixels, torch.cat([pitch, yaw], -1)
 
@@ -163,11 +162,9 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
         batch_size = z.shape[0]
         self.generate_avg_frequencies(rng=kwargs.get('_avg_rng'))
         with torch.no_grad():
-            raw_frequencies, raw_phase_shifts = self.siren.mapping_network(z)
-            frequencies = self.avg_frequencies + psi * (raw_frequencies - self.avg_frequencies)
-            phase_shifts = self.avg_phase_shifts + psi * (raw_phase_shifts - self.avg_phase_shifts)
+            film = self.siren.film_from_latents(z, psi=psi, avg=(self.avg_frequencies, self.avg_phase_shifts))
             pixels, depth, wsum, weights, _, _ = self._render(
-                self._film(frequencies, phase_shifts), batch_size, img_size, fov, ray_start, ray_end, num_steps,
+                film, batch_size, img_size, fov, ray_start, ray_end, num_steps,
                 h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs,
                 staged=True)
             depth_map = depth.reshape(batch_size, img_size, img_size).contiguous().cpu()
@@ -223,9 +220,8 @@ class StyleGenerator3d(ImplicitGenerator3d):
         self._check_no_neural_renderer()
         batch_size = z.shape[0]
         with torch.no_grad():
-            frequencies, phase_shifts = self.siren.mapping_network(z)
             pixels, depth, wsum, _, _, _ = self._render(
-                self._film(frequencies, phase_shifts), batch_size, img_size, fov, ray_start, ray_end, num_steps,
+                self.siren.film_from_latents(z), batch_size, img_size, fov, ray_start, ray_end, num_steps,
                 h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs,
                 staged=True)
             depth_map = depth.reshape(batch_size, img_size, img_size).contiguous().cpu()
@@ -275,16 +271,11 @@ class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
             return self.part_forward(z_geo, z_app, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev,
                                      h_mean, v_mean, hierarchical_sample, sample_dist=None,
                                      lock_view_dependence=False, **kwargs)
-        film = self.siren.film_table(*self._map(z_geo, z_app))
+        film = self.siren.film_from_latents(z_geo, z_app)
         pixels, _, _, _, pitch, yaw = self._render(
             film, batch_size, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean,
             hierarchical_sample, sample_dist, lock_view_dependence, kwargs, staged=False)
         return pixels, torch.cat([pitch, yaw], -1)
-
-    def _map(self, z_geo, z_app):
-        frequencies_geo, phase_shifts_geo = self.siren.geo_mapping_network(z_geo)
-        frequencies_app, phase_shifts_app = self.siren.app_mapping_network(z_app)
-        return frequencies_geo, frequencies_app, phase_shifts_geo, phase_shifts_app
 
     def staged_forward(self, z_geo, z_app, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean,
                        v_mean, psi=1, lock_view_dependence=False, max_batch_size=50000, depth_map=False, near_clip=0,
@@ -292,13 +283,10 @@ class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
         batch_size = z_app.shape[0]
         self.generate_avg_frequencies(rng=kwargs.get('_avg_rng'))
         with torch.no_grad():
-            f_geo, f_app, p_geo, p_app = self._map(z_geo, z_app)
-            f_geo = self.avg_frequencies_geo + psi * (f_geo - self.avg_frequencies_geo)
-            p_geo = self.avg_phase_shifts_geo + psi * (p_geo - self.avg_phase_shifts_geo)
-            f_app = self.avg_frequencies_app + psi * (f_app - self.avg_frequencies_app)
-            p_app = self.avg_phase_shifts_app + psi * (p_app - self.avg_phase_shifts_app)
+            film = self.siren.film_from_latents(z_geo, z_app, psi=psi, avg=(
+                self.avg_frequencies_geo, self.avg_phase_shifts_geo, self.avg_frequencies_app, self.avg_phase_shifts_app))
             pixels, depth, _, _, _, _ = self._render(
-                self.siren.film_table(f_geo, f_app, p_geo, p_app), batch_size, img_size, fov, ray_start, ray_end,
+                film, batch_size, img_size, fov, ray_start, ray_end,
                 num_steps, h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist,
                 lock_view_dependence, kwargs, staged=True)
             depth_map = depth.reshape(batch_size, img_size, img_size).contiguous().cpu()
@@ -339,7 +327,7 @@ class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):
         grad_points = kwargs.get('grad_points', img_size * img_size)
         assert img_size * img_size > grad_points
         batch_size = z_app.shape[0]
-        film = self.siren.film_table(*self._map(z_geo, z_app))
+        film = self.siren.film_from_latents(z_geo, z_app)
         pixels, _, _, _, pitch, yaw = self._render(
             film, batch_size, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean,
             hierarchical_sample, sample_dist, lock_view_dependence, kwargs, staged=False, grad_points=grad_points)

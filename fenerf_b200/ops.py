@@ -329,3 +329,31 @@ def render_forward_stages(module, rd, film, x_lin, y_lin, z_lin, cam2world, rng_
         st.update(points_f=view(off.points_fine, (b, n, s, 3)), z_f=view(off.z_fine, (b, n, s)),
                   raw_f=view(off.raw_fine, (b, n, s, c)))
     return st
+
+
+def mapping_film(net, z, film, first_layer, n_layers, avg=None, psi=1.0):
+    """fenerf_mapping_film: CustomMappingNetwork + `15 f + 30` (+ psi truncation towards `avg` = (avg_frequencies,
+    avg_phase_shifts)) written straight into layers [first_layer, first_layer + n_layers) of the FiLM table
+    `film` (B, L, 2, 256).  Two launches instead of ~15 (no_grad callers only)."""
+    linears = [m for m in net.network if isinstance(m, torch.nn.Linear)]
+    if len(linears) != 5:
+        raise ValueError("mapping network: expected 5 Linear layers, got %d" % len(linears))
+    device = film.device
+    p = _lib.MappingParams()
+    keep = []
+    for i, lin in enumerate(linears):
+        w, b = _prep(lin.weight, device), _prep(lin.bias, device)
+        keep += [w, b]
+        p.weight[i], p.bias[i] = w.data_ptr(), b.data_ptr()
+    p.z_dim, p.hidden_dim = linears[0].in_features, linears[0].out_features
+    z = _prep(z, device)
+    bsz = z.shape[0]
+    h = torch.empty((min(bsz, 32), 256), dtype=torch.float32, device=device)
+    af = ap = None
+    if avg is not None:
+        af, ap = _prep(avg[0].reshape(-1), device), _prep(avg[1].reshape(-1), device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().fenerf_mapping_film(
+            C.byref(p), _chk(z, "z", device), bsz, n_layers, first_layer, film.shape[1], _chk(af, "avg_frequencies", device),
+            _chk(ap, "avg_phase_shifts", device), float(psi), h.data_ptr(), _chk(film, "film", device), _stream(device)))
+    return film

@@ -158,6 +158,15 @@ class FieldSpec:
     double_latent: bool
 
 
+def _fused_mapping_ok(net, z):
+    """The two-launch mapping kernels serve no_grad callers on CUDA with the reference's 256-wide, 3-block network."""
+    if torch.is_grad_enabled() or not z.is_cuda or z.dtype != torch.float32:
+        return False
+    lin = [m for m in net.network if isinstance(m, nn.Linear)]
+    return (len(lin) == 5 and lin[0].out_features == 256 and lin[0].in_features % 4 == 0 and lin[0].in_features <= 512
+            and lin[-1].out_features % 512 == 0)
+
+
 class _FieldBase(nn.Module):
     """Shared host logic: FiLM table assembly, weight packing cache, dispatch to the C-ABI."""
 
@@ -262,6 +271,21 @@ class TALLSIREN(_FieldBase):
         p = phase_shifts.reshape(b, -1, self.hidden_dim)
         return torch.stack([f, p], dim=2).float().contiguous()
 
+    def film_from_latents(self, z, psi=1.0, avg=None):
+        """z -> FiLM table.  Under no_grad on a CUDA device: the fused mapping kernels (fenerf_mapping_film, two
+        launches); otherwise the PyTorch modules, so that autograd reaches the mapping network and the latent.
+        `avg` = (avg_frequencies, avg_phase_shifts) enables the psi truncation of staged_forward."""
+        from .. import ops
+        n = len(self.network) + 1
+        if _fused_mapping_ok(self.mapping_network, z):
+            film = torch.empty((z.shape[0], n, 2, self.hidden_dim), dtype=torch.float32, device=z.device)
+            return ops.mapping_film(self.mapping_network, z, film, 0, n, avg=avg, psi=psi)
+        frequencies, phase_shifts = self.mapping_network(z)
+        if avg is not None:
+            frequencies = avg[0] + psi * (frequencies - avg[0])
+            phase_shifts = avg[1] + psi * (phase_shifts - avg[1])
+        return self.film_table(frequencies, phase_shifts)
+
     def forward(self, input, z, ray_directions, **kwargs):
         frequencies, phase_shifts = self.mapping_network(z)
         return self.forward_with_frequencies_phase_shifts(input, frequencies, phase_shifts, ray_directions, **kwargs)
@@ -340,6 +364,22 @@ class _DoubleLatentField(_FieldBase):
         f = torch.cat([(frequencies_geo * 15 + 30).reshape(b, -1, h), (frequencies_app * 15 + 30).reshape(b, -1, h)], 1)
         p = torch.cat([phase_shifts_geo.reshape(b, -1, h), phase_shifts_app.reshape(b, -1, h)], 1)
         return torch.stack([f, p], dim=2).float().contiguous()
+
+    def film_from_latents(self, z_geo, z_app, psi=1.0, avg=None):
+        """(z_geo, z_app) -> FiLM table (geometry layers first); see TALLSIREN.film_from_latents.
+        `avg` = (avg_frequencies_geo, avg_phase_shifts_geo, avg_frequencies_app, avg_phase_shifts_app)."""
+        from .. import ops
+        n_geo, n_app = len(self.network), len(self.color_layer_sine)
+        if _fused_mapping_ok(self.geo_mapping_network, z_geo) and _fused_mapping_ok(self.app_mapping_network, z_app):
+            film = torch.empty((z_geo.shape[0], n_geo + n_app, 2, self.hidden_dim), dtype=torch.float32, device=z_geo.device)
+            ops.mapping_film(self.geo_mapping_network, z_geo, film, 0, n_geo, avg=None if avg is None else avg[0:2], psi=psi)
+            return ops.mapping_film(self.app_mapping_network, z_app, film, n_geo, n_app, avg=None if avg is None else avg[2:4], psi=psi)
+        f_geo, p_geo = self.geo_mapping_network(z_geo)
+        f_app, p_app = self.app_mapping_network(z_app)
+        if avg is not None:
+            f_geo, p_geo = avg[0] + psi * (f_geo - avg[0]), avg[1] + psi * (p_geo - avg[1])
+            f_app, p_app = avg[2] + psi * (f_app - avg[2]), avg[3] + psi * (p_app - avg[3])
+        return self.film_table(f_geo, f_app, p_geo, p_app)
 
     def forward(self, input, z_geo, z_app, ray_directions, **kwargs):
         frequencies_geo, phase_shifts_geo = self.geo_mapping_network(z_geo)

@@ -258,6 +258,23 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
                           int64_t* inds_dbg, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* ---- mapping network -> FiLM table -------------------------------------------------------------------
+ * CustomMappingNetwork (siren/siren.py:82-102: Linear(z, 256) + LeakyReLU(0.2), 3 x [Linear(256, 256) + LeakyReLU],
+ * Linear(256, n_layers * 512)), the halves split into frequencies / phase shifts (:100-101), the `15 f + 30`
+ * affine (siren.py:165) and, when the averages are given, the psi truncation of staged_forward
+ * (generators.py:143-149): v = avg + psi (v - avg).  Writes layers [first_layer, first_layer + n_layers) of
+ * film (B, n_film_total, 2, 256); a double-latent field calls it once per mapping network.  no_grad only.
+ * h_scratch: min(B, 32) * 256 floats. */
+typedef struct fenerf_mapping_params {
+    const float* weight[5];   /* nn.Linear weights [out][in] fp32, in network order */
+    const float* bias[5];
+    int32_t z_dim;            /* multiple of 4, <= 512 */
+    int32_t hidden_dim;       /* 256 */
+} fenerf_mapping_params;
+int fenerf_mapping_film(const fenerf_mapping_params* net, const float* z, int32_t batch, int32_t n_layers, int32_t first_layer,
+                        int32_t n_film_total, const float* avg_frequencies, const float* avg_phase_shifts, float psi,
+                        float* h_scratch, float* film, void* stream);
+
 /* ---- frame consumers ---------------------------------------------------------------------------------
  * mask2color (train_double_latent_semantic.py:36-55, 66-72): masks (B, K, H, W) -> argmax over K -> the reference's
  * 19-entry colour table -> out (B, 3, H, W) float in 0..255 (classes >= 19 stay black, as in the reference). */

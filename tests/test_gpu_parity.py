@@ -531,6 +531,38 @@ def test_render_script_call_sequence(runs, tmp_path):
     assert rgb.shape[1] == 3 and segmap.shape[1] == img.shape[1] - 3
 
 
+@pytest.mark.parametrize("name,batch", [("a_small", 3), ("b_small", 2), ("h_small", 5), ("a_small", 37)])
+def test_fused_mapping_network_matches_the_modules(name, batch):
+    """fenerf_mapping_film (cluster kernel + wide last layer) against CustomMappingNetwork + film_table in PyTorch,
+    with and without the psi truncation of staged_forward."""
+    case = _cases.CASE_BY_NAME[name]
+    gen = _cases.build_mirror(case, DEV)
+    sir = gen.siren
+    g = torch.Generator(device=DEV).manual_seed(1)
+    zs = [torch.randn(batch, 256, device=DEV, generator=g) for _ in range(_cases.n_latents(case.model))]
+    with torch.no_grad():
+        got = sir.film_from_latents(*zs)
+        if len(zs) == 1:
+            f, p = sir.mapping_network(zs[0])
+            want = sir.film_table(f, p)
+            avg = (f.mean(0, keepdim=True) * 0.9, p.mean(0, keepdim=True) * 1.1)
+            want_t = sir.film_table(avg[0] + 0.7 * (f - avg[0]), avg[1] + 0.7 * (p - avg[1]))
+        else:
+            fg, pg = sir.geo_mapping_network(zs[0]); fa, pa = sir.app_mapping_network(zs[1])
+            want = sir.film_table(fg, fa, pg, pa)
+            avg = (fg.mean(0, keepdim=True), pg.mean(0, keepdim=True) * 1.1, fa.mean(0, keepdim=True) * 0.9, pa.mean(0, keepdim=True))
+            want_t = sir.film_table(avg[0] + 0.7 * (fg - avg[0]), avg[2] + 0.7 * (fa - avg[2]), avg[1] + 0.7 * (pg - avg[1]),
+                                    avg[3] + 0.7 * (pa - avg[3]))
+        got_t = sir.film_from_latents(*zs, psi=0.7, avg=avg)
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max(), float((got - want).abs().max())
+    assert (got_t - want_t).abs().max() <= 2e-5 * want_t.abs().max(), float((got_t - want_t).abs().max())
+    # with autograd on, the PyTorch modules run (the latent / mapping network must stay differentiable)
+    z = zs[0].clone().requires_grad_(True)
+    film = sir.film_from_latents(z, *zs[1:])
+    assert film.requires_grad
+
+
 def test_frame_consumers_match_the_reference_loops():
     """mask2color (train_double_latent_semantic.py:66-72) and save_image's quantisation (fid_evaluation.py:149)."""
     from fenerf_b200 import frames
