@@ -28,6 +28,7 @@ EXPORTS = (
     "fenerf_field_fingerprint", "fenerf_composite_backward", "fenerf_film_forward_stash", "fenerf_gate_backward",
     "fenerf_head_grads", "fenerf_extras_gather", "fenerf_grid_scatter_add", "fenerf_grid_unpack_grad",
     "fenerf_workspace_layout", "fenerf_mask2color", "fenerf_frames_to_u8", "fenerf_mapping_film",
+    "fenerf_guard_stats",
 )
 
 
@@ -53,6 +54,10 @@ class RenderDesc(C.Structure):
                 ("fill_mode", C.c_int32), ("fill_color", C.c_float), ("softmax_label", C.c_int32),
                 ("lock_view_dependence", C.c_int32), ("precision", C.c_int32),
                 ("noise_std", C.c_float), ("tan_half_fov", C.c_float), ("guard_tau", C.c_float)]
+
+
+class GuardReport(C.Structure):
+    _fields_ = [("refined", C.c_int32), ("max_abs_delta", C.c_float), ("sign_flips", C.c_int32), ("tau", C.c_float)]
 
 
 class MappingParams(C.Structure):
@@ -106,6 +111,8 @@ def _declare(lib):
     lib.fenerf_grid_scatter_add.argtypes = [P(FieldDesc), vp, vp, i32, i64, vp, i32, vp]
     lib.fenerf_grid_unpack_grad.restype = C.c_int
     lib.fenerf_grid_unpack_grad.argtypes = [P(FieldDesc), vp, vp, vp, vp]
+    lib.fenerf_guard_stats.restype = C.c_int
+    lib.fenerf_guard_stats.argtypes = [vp, P(GuardReport), vp]
     lib.fenerf_mapping_film.restype = C.c_int
     lib.fenerf_mapping_film.argtypes = [P(MappingParams), vp, i32, i32, i32, i32, vp, vp, C.c_float, vp, vp, vp]
     lib.fenerf_mask2color.restype = C.c_int

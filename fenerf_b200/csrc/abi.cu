@@ -14,7 +14,7 @@ using namespace fn;
 namespace {
 
 struct Workspace {
-    size_t points_c, z_c, dirs, origins, raw_c, z_f, points_f, raw_f, guard, total;
+    size_t stats, points_c, z_c, dirs, origins, raw_c, z_f, points_f, raw_f, guard, total;
 };
 
 Workspace plan_workspace(const fenerf_render_desc* rd, int C) {
@@ -23,6 +23,7 @@ Workspace plan_workspace(const fenerf_render_desc* rd, int C) {
     size_t pc = n_rays * rd->num_steps;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = fn_align_up(off + bytes, 256); return o; };
+    w.stats = take(64);               // always at offset 0: fenerf_guard_stats
     w.points_c = take(pc * 3 * 4);
     w.z_c = take(pc * 4);
     w.dirs = take(n_rays * 3 * 4);
@@ -165,6 +166,18 @@ size_t fenerf_workspace_bytes(const fenerf_render_desc* rd, const fenerf_field_d
     return plan_workspace(rd, field->out_dim).total;
 }
 
+int fenerf_guard_stats(const void* workspace, fenerf_guard_report* out, void* stream) {
+    FN_REQUIRE(workspace && out, "NULL argument");
+    int32_t raw[4];
+    FN_CUDA_OK(cudaMemcpyAsync(raw, workspace, sizeof(raw), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    FN_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    out->refined = raw[0];
+    out->max_abs_delta = *reinterpret_cast<const float*>(&raw[1]);
+    out->sign_flips = raw[2];
+    out->tau = *reinterpret_cast<const float*>(&raw[3]);
+    return 0;
+}
+
 int fenerf_workspace_layout(const fenerf_render_desc* rd, const fenerf_field_desc* field, fenerf_workspace_offsets* out) {
     if (int e = check_render_desc(rd)) return e;
     FN_REQUIRE(field && out, "NULL argument");
@@ -216,7 +229,7 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
         const int n_samples = rd->hierarchical ? 2 * rd->num_steps : rd->num_steps;
         if (int e = guard_refine(L, (const unsigned char*)packed, points_c, dirs, film, rd->batch, rays, rd->num_steps,
                                  rd->lock_view_dependence, tau, noise_f ? noise_f + (n_samples - 1) : nullptr, n_samples,
-                                 rd->noise_std, raw_c, guard, st)) return e;
+                                 rd->noise_std, raw_c, guard, (int32_t*)(ws + w.stats), st)) return e;
     }
     if (rd->hierarchical) {
         if (int e = resample(rd, C, raw_c, z_c, dirs, origins, noise_c, rng_u, z_f, points_f, (long long*)inds_dbg, st,

@@ -93,7 +93,7 @@ int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const flo
 int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                  const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
                  const float* noise_far, long long noise_stride, float noise_std,
-                 float* raw, int32_t* scratch_idx, cudaStream_t st);
+                 float* raw, int32_t* scratch_idx, int32_t* stats, cudaStream_t st);
 int camera_poses(int n, int mode, float h_std, float v_std, float h_mean, float v_mean, const float* draw_theta,
                  const float* draw_phi, float* c2w, float* pitch, float* yaw, cudaStream_t st);
 int ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_lin, const float* z_lin,

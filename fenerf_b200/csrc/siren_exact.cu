@@ -43,6 +43,7 @@ struct ExactArgs {
     int dir_group;
     int lock_dirs;
     int sigma_only;      // stop after the density head: out[..., C-1] only (GUARD refinement, density grids)
+    int32_t* guard_stats;  // GUARD self-check (fenerf_b200.h: fenerf_guard_stats) or NULL
 };
 
 // P = points per thread (4: dense 64-point tiles; 1: 16-point tiles for the sparse GUARD gather, where
@@ -280,8 +281,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
                     float r = o == 0 ? __ldg(sw + FN_H) : __ldg(lw + FENERF_MAX_LABEL * FN_H + (o - 1));
                     for (int k = 0; k < FN_H; ++k) r = fmaf(s.A[k][pt], __ldg(w + k), r);
                     long long flat = s.flat[pt];
-                    if (flat >= 0) a.out[flat * C + (o == 0 ? C - 1 : o - 1)] = r;
+                    if (flat >= 0) {
+                        if (kGather && a.guard_stats && o == 0) {
+                            // how far the tcgen05 density was from this fp32 one, and whether its sign was wrong: the
+                            // margin of the GUARD threshold, measured on the very weights / points being rendered
+                            const float old = a.out[flat * C + C - 1];
+                            atomicMax(a.guard_stats + 1, __float_as_int(fabsf(r - old)));
+                            if ((old > 0.f) != (r > 0.f)) atomicAdd(a.guard_stats + 2, 1);
+                        }
+                        a.out[flat * C + (o == 0 ? C - 1 : o - 1)] = r;
+                    }
                 }
+                if (kGather && a.guard_stats && tile == 0 && tid == 0) a.guard_stats[0] = n_only;
                 __syncthreads();
                 if (a.sigma_only) break;          // the colour branch does not feed the density
             }
@@ -316,7 +327,7 @@ int siren_points_exact(const FnLayout& L, const unsigned char* packed, const flo
     constexpr int TM = 64;
     ExactArgs a;
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.only_idx = only_idx; a.out = out;
-    a.n_only_dev = nullptr;
+    a.n_only_dev = nullptr; a.guard_stats = nullptr;
     a.ppb = ppb; a.n_only = n_only; a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs;
     a.sigma_only = sigma_only ? 1 : 0;
     a.tiles_per_batch = (ppb + TM - 1) / TM;
@@ -348,7 +359,8 @@ int siren_points_exact(const FnLayout& L, const unsigned char* packed, const flo
 namespace {
 __global__ void guard_scan_kernel(const float* __restrict__ raw, long long n_rays, int S, int C, float tau,
                                   const float* __restrict__ noise_far, long long noise_stride, float noise_std,
-                                  int32_t* __restrict__ count, int32_t* __restrict__ list) {
+                                  int32_t* __restrict__ count, int32_t* __restrict__ list, int32_t* __restrict__ stats) {
+    if (stats && blockIdx.x == 0 && threadIdx.x == 0) stats[3] = __float_as_int(tau);
     for (long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x; ray < n_rays;
          ray += (long long)gridDim.x * blockDim.x) {
         long long pt = ray * S + (S - 1);
@@ -367,21 +379,25 @@ __global__ void guard_scan_kernel(const float* __restrict__ raw, long long n_ray
 int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                  const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
                  const float* noise_far, long long noise_stride, float noise_std,
-                 float* raw, int32_t* scratch_idx, cudaStream_t st) {
+                 float* raw, int32_t* scratch_idx, int32_t* stats, cudaStream_t st) {
     long long n_rays = rays_per_batch * batch;
     FN_REQUIRE(n_rays * num_steps < 2147483647LL, "too many points for the 32-bit guard list");
     FN_CUDA_OK(cudaMemsetAsync(scratch_idx, 0, sizeof(int32_t), st));
     int threads = 256;
     long long want = (n_rays + threads - 1) / threads;
     int blocks = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+    if (stats) FN_CUDA_OK(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st));
     guard_scan_kernel<<<blocks, threads, 0, st>>>(raw, n_rays, num_steps, L.out_dim, tau, noise_far, noise_stride, noise_std,
-                                                  scratch_idx, scratch_idx + 1);
+                                                  scratch_idx, scratch_idx + 1, stats);
     FN_LAUNCH_OK("guard_scan_kernel");
     ExactArgs a;
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = raw;
     a.only_idx = scratch_idx + 1; a.n_only_dev = scratch_idx; a.n_only = 0; a.n_items = 0;
     a.ppb = rays_per_batch * num_steps; a.tiles_per_batch = 1; a.dir_group = num_steps; a.lock_dirs = lock_dirs;
     a.sigma_only = 1;      // only the sign of the far sample's density matters; its colour stays the tcgen05 one
+    a.guard_stats = stats;
+    // (stats[0..2] were zeroed and stats[3] = tau written by guard_scan_kernel's launch above: no host memory is
+    // touched here, so the whole refinement can sit inside a captured CUDA graph)
     // 16-point tiles: the guard list is a few thousand points at most, so spread it over every SM and
     // keep each tile's latency low (one wave of 64-point tiles idles most of the chip for ~0.3 ms)
     size_t smem = sizeof(Smem<1>);

@@ -14,10 +14,12 @@ Hidden keyword extras (never passed by the reference's callers, used by tests an
   precision   'exact' | 'fast' | 'guard' (default: ops.default_precision())
   _debug      dict that receives intermediate tensors (inds, depth, weights_sum, poses)
 """
+import warnings
+
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import _lib, ops
 from . import volumetric_rendering as vr
 
 
@@ -77,7 +79,7 @@ class _RenderSkeleton:
                 fill_mode=kwargs.get('fill_mode', None) if staged else None,
                 fill_color=kwargs.get('fill_color', 'black'), softmax_label=self.softmax_label,
                 lock_view_dependence=lock_view_dependence, precision=kwargs.get('precision'),
-                guard_tau=kwargs.get('guard_tau', 0.0))
+                guard_tau=kwargs.get('guard_tau', getattr(self.siren, '_guard_tau', 0.0)))
             debug = kwargs.get('_debug')
             fill_mode = kwargs.get('fill_mode', None) if staged else None
             wants_per_sample_weights = staged and fill_mode in (None, 'debug', 'seg_padding_background')
@@ -87,6 +89,22 @@ class _RenderSkeleton:
                     rng_noise_c, rng_u, rng_noise_f, want_depth=staged or debug is not None,
                     want_weights_sum=staged or debug is not None, want_weights=wants_per_sample_weights,
                     want_inds=debug is not None)
+                if staged and rd.precision == _lib.PRECISION['guard'] and clamp_mode == 'relu':
+                    # GUARD self-check (the staged methods synchronise anyway): the refinement measured how far the tcgen05
+                    # far-sample densities were from fp32 ON THESE WEIGHTS.  The default threshold was calibrated on the
+                    # reference's random initialisation; if the measured error eats more than a third of it, widen it (it
+                    # sticks to this field for later calls) and render this call again.
+                    rep = ops.guard_stats(device)
+                    if rep is not None and rep['refined'] > 0 and rep['max_abs_delta'] > rep['tau'] / 3:
+                        new_tau = max(4.0 * rep['max_abs_delta'], rep['tau'])
+                        warnings.warn("fenerf_b200: fp16 density error %.3g is within 3x of guard_tau %.3g on these weights; "
+                                      "guard_tau -> %.3g" % (rep['max_abs_delta'], rep['tau'], new_tau))
+                        self.siren._guard_tau = new_tau
+                        rd.guard_tau = new_tau
+                        pixels, depth, wsum, weights, inds = ops.render_forward(
+                            self.siren, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb.contiguous(),
+                            rng_noise_c, rng_u, rng_noise_f, want_depth=True, want_weights_sum=True,
+                            want_weights=wants_per_sample_weights, want_inds=debug is not None)
                 if debug is not None:
                     debug.update(depth=depth, weights_sum=wsum, inds=inds, pitch=pitch, yaw=yaw, cam2world=cam2world)
         if with_grad:

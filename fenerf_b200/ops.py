@@ -259,6 +259,22 @@ def _workspace(device, nbytes):
     return ws
 
 
+DEFAULT_GUARD_TAU = 1.5e-3
+
+
+def guard_stats(device):
+    """The GUARD self-check of the last render_forward on the current stream (fenerf_guard_stats): how far the tcgen05
+    far-sample densities were from their fp32 re-evaluation.  Synchronises the stream."""
+    device = torch.device(device)
+    ws = _WORKSPACES.get((device, torch.cuda.current_stream(device).cuda_stream))
+    if ws is None:
+        return None
+    rep = _lib.GuardReport()
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().fenerf_guard_stats((ws.data_ptr() + 255) // 256 * 256, C.byref(rep), _stream(device)))
+    return dict(refined=rep.refined, max_abs_delta=rep.max_abs_delta, sign_flips=rep.sign_flips, tau=rep.tau)
+
+
 def render_forward(module, rd, film, x_lin, y_lin, z_lin, cam2world, rng_perturb, rng_noise_c, rng_u, rng_noise_f,
                    want_depth=True, want_weights_sum=True, want_weights=False, want_inds=False):
     """One call into fenerf_render_forward: the whole render after the mapping network."""

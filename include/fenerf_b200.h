@@ -224,6 +224,21 @@ int fenerf_composite(const fenerf_render_desc* rd, int32_t out_dim, const float*
 /* Scratch bytes fenerf_render_forward needs for this (render, field) pair. */
 size_t fenerf_workspace_bytes(const fenerf_render_desc* rd, const fenerf_field_desc* field);
 
+/* GUARD self-check.  The refinement pass knows, for every far sample it re-evaluates in fp32, what the tcgen05
+ * density was: the largest |difference| and the number of wrong signs are the measured margin of `guard_tau` on
+ * the weights and points actually rendered (the default tau was calibrated on the reference's random
+ * initialisation; trained weights can have larger activations).  A refinement is only trustworthy while
+ * max_abs_delta stays well below tau -- the host mirror raises tau and re-renders when it exceeds tau / 3.
+ * Reads 16 bytes at the start of the workspace of the LAST fenerf_render_forward (precision GUARD) on `stream`
+ * and synchronises that stream. */
+typedef struct fenerf_guard_report {
+    int32_t refined;        /* far samples re-evaluated (|sigma + noise| < tau) */
+    float   max_abs_delta;  /* max |sigma_fp32 - sigma_tcgen05| over them */
+    int32_t sign_flips;     /* of which the tcgen05 sign was wrong (these are what the GUARD fixes) */
+    float   tau;            /* the threshold that was used */
+} fenerf_guard_report;
+int fenerf_guard_stats(const void* workspace, fenerf_guard_report* out, void* stream);
+
 /* Where fenerf_render_forward leaves its intermediates inside the caller's workspace (byte offsets): the sample
  * points and depths of both passes, ray directions / origins and the raw field outputs -- what the backward
  * needs, and what a debugger wants to look at.  Valid after a fenerf_render_forward with the same (rd, field);

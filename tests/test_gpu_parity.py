@@ -582,6 +582,33 @@ def test_frame_consumers_match_the_reference_loops():
         assert torch.equal(u8[b], oracle.save_image_bytes(img[b, -3:]))
 
 
+def test_guard_self_check_widens_the_threshold_on_large_weights():
+    """The GUARD threshold was calibrated on the reference's initialisation.  The refinement
+    reports max |sigma_fp32 - sigma_tcgen05| over the samples it re-evaluates; staged_* widens tau when that error
+    comes within 3x of it.  Scaling the density head by 30 scales the fp16 error with it."""
+    import warnings
+    case = _cases.CASE_BY_NAME["a_small"]
+    gen = _cases.build_mirror(case, DEV)
+    z = torch.randn(2, 256, device=DEV)
+    with torch.no_grad():
+        torch.manual_seed(1)
+        gen.staged_forward(z, **case.cfg)
+        rep = ops.guard_stats(DEV)
+        assert rep["refined"] > 0 and 0 < rep["max_abs_delta"] < rep["tau"] / 3 and abs(rep["tau"] - 1.5e-3) < 1e-9
+        assert not hasattr(gen.siren, "_guard_tau")
+        gen.siren.final_layer.weight.mul_(30.0)
+        gen.siren.final_layer.bias.mul_(30.0)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            torch.manual_seed(1)
+            a = gen.staged_forward(z, **case.cfg)[0].cpu()
+        assert any("guard_tau" in str(x.message) for x in w), "no widening on 30x weights"
+        assert gen.siren._guard_tau > 1.5e-3
+        torch.manual_seed(1)
+        b = gen.staged_forward(z, **dict(case.cfg, precision="exact"))[0].cpu()
+    assert ((a - b).abs() > 1e-3).float().mean() < 0.02     # the widened guard keeps the step function right
+
+
 def test_repack_after_inplace_weight_update():
     case = _cases.CASE_BY_NAME["a_small"]
     gen = _cases.build_mirror(case, DEV)
