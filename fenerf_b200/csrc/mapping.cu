@@ -4,24 +4,20 @@
 // `frequencies * 15 + 30` affine and the psi truncation of staged_forward (generators.py:143-149, 556-564) for
 // no_grad callers.  In PyTorch this is 5 cuBLAS gemv + 4 leaky_relu + ~6 elementwise / cat / stack kernels per
 // mapping network (~60 us of launches for a 10 us problem; at 64x64 that is a fifth of the step).
-//   mapping_hidden_kernel   one thread-block CLUSTER of 8 CTAs runs the four 256-wide hidden layers for the whole
-//                           batch: a warp owns 4 output features, reads their weight rows once (coalesced float4)
-//                           and reuses them across the batch; every CTA broadcasts its 32 outputs into the other
-//                           CTAs' shared memory (DSMEM) and the cluster syncs once per layer
+//   mapping_hidden_kernel   one CTA of 32 warps runs the four 256-wide hidden layers for the whole batch: a warp owns 8
+//                           output features, reads their weight rows coalesced and reuses them across the batch (a
+//                           thread-block-cluster version with DSMEM broadcasts measured 52 us: the cluster barriers and
+//                           remote stores cost more than the 256 KB per layer one SM has to read)
 //   mapping_out_kernel      the wide last layer (256 -> n_layers * 512) over all SMs, writing the FiLM table
 //                           [15 f + 30, phase] directly (with the optional psi truncation towards the averages)
 // Pure fp32 FFMA; sums run in a different order than cuBLAS' gemv (~1e-7 relative on the table).
 #include "common.cuh"
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 namespace fn {
 
 namespace {
 
 constexpr int kMaxB = 32;         // batch elements per launch (the host loops over larger batches)
-constexpr int kClusterSize = 8;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct HiddenArgs {
@@ -32,54 +28,55 @@ struct HiddenArgs {
     int B, z_dim;
 };
 
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(256) mapping_hidden_kernel(HiddenArgs a) {
-    extern __shared__ __align__(16) float xs[];          // [2][B][512]: layer input (z_dim <= 512, then 256)
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
+// One CTA of 32 warps: a warp owns 8 output features per layer, reads their weight rows coalesced (a 256-wide row is
+// one float4 per lane twice) and reuses them for up to kChunkB batch elements held in registers.
+constexpr int kChunkB = 8;
+
+__global__ void __launch_bounds__(1024) mapping_hidden_kernel(HiddenArgs a) {
+    extern __shared__ __align__(16) float xs[];          // [2][B][512]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B = a.B;
     float* x0 = xs;
     float* x1 = xs + (size_t)B * 512;
     for (int i = threadIdx.x; i < B * a.z_dim; i += blockDim.x) x0[(i / a.z_dim) * 512 + (i % a.z_dim)] = a.z[i];
-    cluster.sync();
+    __syncthreads();
     int K = a.z_dim;
     for (int layer = 0; layer < 4; ++layer) {
         const float* W = a.w[layer];
         const float* bias = a.b[layer];
-        float* xin = (layer & 1) ? x1 : x0;
+        const float* xin = (layer & 1) ? x1 : x0;
         float* xout = (layer & 1) ? x0 : x1;
-#pragma unroll 1
-        for (int o = 0; o < 4; ++o) {
-            const int f = rank * 32 + warp * 4 + o;
-            float acc[kMaxB];
+        for (int o = 0; o < 8; ++o) {
+            const int f = warp * 8 + o;
+            for (int b0 = 0; b0 < B; b0 += kChunkB) {
+                float acc[kChunkB];
 #pragma unroll
-            for (int b = 0; b < kMaxB; ++b) acc[b] = 0.f;
-            for (int k = lane * 4; k < K; k += 128) {
-                const float4 wv = *reinterpret_cast<const float4*>(W + (size_t)f * K + k);
+                for (int b = 0; b < kChunkB; ++b) acc[b] = 0.f;
+                for (int k = lane * 4; k < K; k += 128) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)f * K + k));
 #pragma unroll
-                for (int b = 0; b < kMaxB; ++b)
-                    if (b < B) {
-                        const float4 xv = *reinterpret_cast<const float4*>(xin + b * 512 + k);
-                        acc[b] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[b]))));
+                    for (int b = 0; b < kChunkB; ++b)
+                        if (b0 + b < B) {
+                            const float4 xv = *reinterpret_cast<const float4*>(xin + (b0 + b) * 512 + k);
+                            acc[b] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[b]))));
+                        }
+                }
+#pragma unroll
+                for (int b = 0; b < kChunkB; ++b)
+                    if (b0 + b < B) {
+                        float v = acc[b];
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+                        v += bias[f];
+                        v = v > 0.f ? v : 0.2f * v;                         // LeakyReLU(0.2)
+                        if (lane == 0) {
+                            if (layer == 3) a.h_out[(b0 + b) * 256 + f] = v;
+                            else xout[(b0 + b) * 512 + f] = v;
+                        }
                     }
             }
-#pragma unroll
-            for (int b = 0; b < kMaxB; ++b)
-                if (b < B) {
-                    float v = acc[b];
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
-                    v += bias[f];
-                    v = v > 0.f ? v : 0.2f * v;                         // LeakyReLU(0.2)
-                    if (layer == 3) {
-                        if (lane == 0) a.h_out[b * 256 + f] = v;
-                    } else if (lane < kClusterSize) {
-                        float* remote = cluster.map_shared_rank(xout, lane);   // one lane per destination CTA
-                        remote[b * 512 + f] = v;
-                    }
-                }
         }
-        cluster.sync();
+        __syncthreads();
         K = 256;
     }
 }
@@ -142,7 +139,7 @@ int mapping_film(const float* const* w, const float* const* b, const float* z, i
         const size_t smem_h = (size_t)2 * nb * 512 * sizeof(float);
         static std::atomic<int> set_h[kMaxDevices];
         if (smem_h > 48 * 1024) FN_CUDA_OK(ensure_dynamic_smem(mapping_hidden_kernel, set_h, (int)smem_h));
-        mapping_hidden_kernel<<<kClusterSize, 256, smem_h, st>>>(ha);
+        mapping_hidden_kernel<<<1, 1024, smem_h, st>>>(ha);
         FN_LAUNCH_OK("mapping_hidden_kernel");
         OutArgs oa;
         oa.w = w[4]; oa.b = b[4]; oa.h = h_scratch; oa.avg_f = avg_f; oa.avg_p = avg_p;

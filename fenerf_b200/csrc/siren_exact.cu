@@ -368,7 +368,10 @@ __global__ void guard_scan_kernel(const float* __restrict__ raw, long long n_ray
         // the step of the final compositing sits at sigma + noise * noise_std = 0 (volumetric_rendering.py:27-32);
         // the far sample is the last one after the merge, so its noise is draw #6 at [ray, n_samples - 1]
         float pre = noise_far ? __fadd_rn(sig, __fmul_rn(noise_far[ray * noise_stride], noise_std)) : sig;
-        if (fabsf(pre) < tau || !isfinite(sig)) {
+        // every 512th ray is a PROBE: re-evaluated whatever its density, so that the self-check statistics
+        // (fenerf_guard_stats) see the fp16 error even when it is larger than tau (then few samples fall below tau and
+        // the flagged ones alone would say nothing)
+        if (fabsf(pre) < tau || !isfinite(sig) || (ray & 511) == 5) {
             int slot = atomicAdd(count, 1);
             list[slot] = (int32_t)pt;
         }

@@ -418,7 +418,8 @@ def test_part_forward_ray_subset_training():
     # and the no_grad flavour of the same call renders the same frames
     with torch.no_grad():
         px2, _ = gen(*[z.detach() for z in latents], **dict(case.cfg, grad_points=int(gold["grad_points"]), _rng=ReplayRng(draws, DEV)))
-    assert torch.equal(px2, pixels.detach())
+    # (not bit-equal: under no_grad the FiLM table comes from the fused mapping kernels, with autograd from the modules)
+    assert (px2 - pixels.detach()).abs().max() <= 1e-4
 
 
 def test_backward_under_autocast_and_gradscaler():
