@@ -51,6 +51,18 @@ int check_render_desc(const fenerf_render_desc* rd) {
     return 0;
 }
 
+// ---- diagnostics: per-stage CUDA-event timing of fenerf_render_forward (warm, in-step numbers; ncu's are cold) ----
+constexpr int kStages = 6;       // ray_setup, field(coarse), guard, resample, field(fine), composite
+bool g_stage_timing = false;
+cudaEvent_t g_stage_ev[kStages + 1];
+
+void stage_mark(int i, cudaStream_t st) {
+    if (!g_stage_timing) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    cudaEventRecord(g_stage_ev[i], st);
+}
+
 int run_field(const FnLayout& L, const void* packed, const float* points, const float* dirs, const float* film,
               int batch, long long ppb, int dir_group, int lock_dirs, int precision, float* out, cudaStream_t st,
               int sigma_only = 0) {
@@ -166,6 +178,24 @@ size_t fenerf_workspace_bytes(const fenerf_render_desc* rd, const fenerf_field_d
     return plan_workspace(rd, field->out_dim).total;
 }
 
+int fenerf_debug_stage_times(int32_t enable, float* ms_out) {
+    if (enable && !g_stage_timing) {
+        for (int i = 0; i <= kStages; ++i) FN_CUDA_OK(cudaEventCreate(&g_stage_ev[i]));
+        g_stage_timing = true;
+        return 0;
+    }
+    if (!enable && g_stage_timing) {
+        g_stage_timing = false;
+        for (int i = 0; i <= kStages; ++i) cudaEventDestroy(g_stage_ev[i]);
+        return 0;
+    }
+    if (g_stage_timing && ms_out) {
+        FN_CUDA_OK(cudaEventSynchronize(g_stage_ev[kStages]));
+        for (int i = 0; i < kStages; ++i) FN_CUDA_OK(cudaEventElapsedTime(ms_out + i, g_stage_ev[i], g_stage_ev[i + 1]));
+    }
+    return 0;
+}
+
 int fenerf_guard_stats(const void* workspace, fenerf_guard_report* out, void* stream) {
     FN_REQUIRE(workspace && out, "NULL argument");
     int32_t raw[4];
@@ -221,9 +251,12 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
     const float* noise_c = rd->noise_std != 0.f ? rng_noise_c : nullptr;
     const float* noise_f = rd->noise_std != 0.f ? rng_noise_f : nullptr;
 
+    stage_mark(0, st);
     if (int e = ray_setup(rd, x_lin, y_lin, z_lin, cam2world, rng_perturb, points_c, z_c, dirs, origins, st)) return e;
+    stage_mark(1, st);
     if (int e = run_field(L, packed, points_c, dirs, film, rd->batch, ppb, rd->num_steps, rd->lock_view_dependence,
                           rd->precision, raw_c, st)) return e;
+    stage_mark(2, st);
     if (rd->precision == FENERF_PRECISION_GUARD) {
         float tau = rd->guard_tau > 0.f ? rd->guard_tau : 1.5e-3f;
         const int n_samples = rd->hierarchical ? 2 * rd->num_steps : rd->num_steps;
@@ -231,15 +264,22 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
                                  rd->lock_view_dependence, tau, noise_f ? noise_f + (n_samples - 1) : nullptr, n_samples,
                                  rd->noise_std, raw_c, guard, (int32_t*)(ws + w.stats), st)) return e;
     }
+    stage_mark(3, st);
     if (rd->hierarchical) {
         if (int e = resample(rd, C, raw_c, z_c, dirs, origins, noise_c, rng_u, z_f, points_f, (long long*)inds_dbg, st,
                              /*sort_fine=*/1)) return e;
+        stage_mark(4, st);
         if (int e = run_field(L, packed, points_f, dirs, film, rd->batch, ppb, rd->num_steps, rd->lock_view_dependence,
                               rd->precision, raw_f, st)) return e;
+    } else {
+        stage_mark(4, st);
     }
+    stage_mark(5, st);
     // both sample lists are depth-sorted here: one thread per ray, accumulators in registers (composite.cu)
-    return composite_sorted(rd, C, raw_c, z_c, rd->hierarchical ? raw_f : nullptr, rd->hierarchical ? z_f : nullptr, noise_f,
-                            pixels, depth, weights_sum, weights, st);
+    const int rc = composite_sorted(rd, C, raw_c, z_c, rd->hierarchical ? raw_f : nullptr, rd->hierarchical ? z_f : nullptr,
+                                    noise_f, pixels, depth, weights_sum, weights, st);
+    stage_mark(6, st);
+    return rc;
 }
 
 int fenerf_mapping_film(const fenerf_mapping_params* net, const float* z, int32_t batch, int32_t n_layers, int32_t first_layer,

@@ -4,7 +4,7 @@
 // `frequencies * 15 + 30` affine and the psi truncation of staged_forward (generators.py:143-149, 556-564) for
 // no_grad callers.  In PyTorch this is 5 cuBLAS gemv + 4 leaky_relu + ~6 elementwise / cat / stack kernels per
 // mapping network (~60 us of launches for a 10 us problem; at 64x64 that is a fifth of the step).
-//   mapping_hidden_kernel   one CTA of 32 warps runs the four 256-wide hidden layers for the whole batch: a warp owns 8
+//   mapping_hidden_kernel   one CTA of 8 warps runs the four 256-wide hidden layers for the whole batch: a warp owns 32
 //                           output features, reads their weight rows coalesced and reuses them across the batch (a
 //                           thread-block-cluster version with DSMEM broadcasts measured 52 us: the cluster barriers and
 //                           remote stores cost more than the 256 KB per layer one SM has to read)
@@ -28,11 +28,11 @@ struct HiddenArgs {
     int B, z_dim;
 };
 
-// One CTA of 32 warps: a warp owns 8 output features per layer, reads their weight rows coalesced (a 256-wide row is
+// One CTA of 8 warps: a warp owns 32 output features per layer, reads their weight rows coalesced (a 256-wide row is
 // one float4 per lane twice) and reuses them for up to kChunkB batch elements held in registers.
 constexpr int kChunkB = 8;
 
-__global__ void __launch_bounds__(1024) mapping_hidden_kernel(HiddenArgs a) {
+__global__ void __launch_bounds__(256) mapping_hidden_kernel(HiddenArgs a) {
     extern __shared__ __align__(16) float xs[];          // [2][B][512]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B = a.B;
@@ -46,20 +46,37 @@ __global__ void __launch_bounds__(1024) mapping_hidden_kernel(HiddenArgs a) {
         const float* bias = a.b[layer];
         const float* xin = (layer & 1) ? x1 : x0;
         float* xout = (layer & 1) ? x0 : x1;
+        // a warp owns 32 output features, in 4 groups of 8; a group's weight rows are requested up front (8 rows x K/128
+        // float4 per lane: 16 independent loads at K = 256) -- one memory latency per group instead of one per row
+#pragma unroll 1
+        for (int og = 0; og < 4; ++og) {
+        float4 wreg[8][4];
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int k = lane * 4 + it * 128;
+                wreg[o][it] = k < K ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(warp * 32 + og * 8 + o) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
         for (int o = 0; o < 8; ++o) {
-            const int f = warp * 8 + o;
+            const int f = warp * 32 + og * 8 + o;
             for (int b0 = 0; b0 < B; b0 += kChunkB) {
                 float acc[kChunkB];
 #pragma unroll
                 for (int b = 0; b < kChunkB; ++b) acc[b] = 0.f;
-                for (int k = lane * 4; k < K; k += 128) {
-                    const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)f * K + k));
 #pragma unroll
-                    for (int b = 0; b < kChunkB; ++b)
-                        if (b0 + b < B) {
-                            const float4 xv = *reinterpret_cast<const float4*>(xin + (b0 + b) * 512 + k);
-                            acc[b] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[b]))));
-                        }
+                for (int it = 0; it < 4; ++it) {
+                    const int k = lane * 4 + it * 128;
+                    if (k < K) {
+                        const float4 wv = wreg[o][it];
+#pragma unroll
+                        for (int b = 0; b < kChunkB; ++b)
+                            if (b0 + b < B) {
+                                const float4 xv = *reinterpret_cast<const float4*>(xin + (b0 + b) * 512 + k);
+                                acc[b] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[b]))));
+                            }
+                    }
                 }
 #pragma unroll
                 for (int b = 0; b < kChunkB; ++b)
@@ -75,6 +92,7 @@ __global__ void __launch_bounds__(1024) mapping_hidden_kernel(HiddenArgs a) {
                         }
                     }
             }
+        }
         }
         __syncthreads();
         K = 256;
@@ -139,7 +157,7 @@ int mapping_film(const float* const* w, const float* const* b, const float* z, i
         const size_t smem_h = (size_t)2 * nb * 512 * sizeof(float);
         static std::atomic<int> set_h[kMaxDevices];
         if (smem_h > 48 * 1024) FN_CUDA_OK(ensure_dynamic_smem(mapping_hidden_kernel, set_h, (int)smem_h));
-        mapping_hidden_kernel<<<1, 1024, smem_h, st>>>(ha);
+        mapping_hidden_kernel<<<1, 256, smem_h, st>>>(ha);
         FN_LAUNCH_OK("mapping_hidden_kernel");
         OutArgs oa;
         oa.w = w[4]; oa.b = b[4]; oa.h = h_scratch; oa.avg_f = avg_f; oa.avg_p = avg_p;

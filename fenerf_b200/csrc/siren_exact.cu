@@ -359,7 +359,8 @@ int siren_points_exact(const FnLayout& L, const unsigned char* packed, const flo
 namespace {
 __global__ void guard_scan_kernel(const float* __restrict__ raw, long long n_rays, int S, int C, float tau,
                                   const float* __restrict__ noise_far, long long noise_stride, float noise_std,
-                                  int32_t* __restrict__ count, int32_t* __restrict__ list, int32_t* __restrict__ stats) {
+                                  int32_t* __restrict__ count, int32_t* __restrict__ list, int32_t* __restrict__ stats,
+                                  long long probe_stride) {
     if (stats && blockIdx.x == 0 && threadIdx.x == 0) stats[3] = __float_as_int(tau);
     for (long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x; ray < n_rays;
          ray += (long long)gridDim.x * blockDim.x) {
@@ -368,10 +369,10 @@ __global__ void guard_scan_kernel(const float* __restrict__ raw, long long n_ray
         // the step of the final compositing sits at sigma + noise * noise_std = 0 (volumetric_rendering.py:27-32);
         // the far sample is the last one after the merge, so its noise is draw #6 at [ray, n_samples - 1]
         float pre = noise_far ? __fadd_rn(sig, __fmul_rn(noise_far[ray * noise_stride], noise_std)) : sig;
-        // every 512th ray is a PROBE: re-evaluated whatever its density, so that the self-check statistics
+        // ~128 rays per launch are PROBES: re-evaluated whatever their density, so that the self-check statistics
         // (fenerf_guard_stats) see the fp16 error even when it is larger than tau (then few samples fall below tau and
         // the flagged ones alone would say nothing)
-        if (fabsf(pre) < tau || !isfinite(sig) || (ray & 511) == 5) {
+        if (fabsf(pre) < tau || !isfinite(sig) || (ray % probe_stride) == 0) {
             int slot = atomicAdd(count, 1);
             list[slot] = (int32_t)pt;
         }
@@ -391,7 +392,7 @@ int guard_refine(const FnLayout& L, const unsigned char* packed, const float* po
     int blocks = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
     if (stats) FN_CUDA_OK(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st));
     guard_scan_kernel<<<blocks, threads, 0, st>>>(raw, n_rays, num_steps, L.out_dim, tau, noise_far, noise_stride, noise_std,
-                                                  scratch_idx, scratch_idx + 1, stats);
+                                                  scratch_idx, scratch_idx + 1, stats, n_rays / 128 > 0 ? n_rays / 128 : 1);
     FN_LAUNCH_OK("guard_scan_kernel");
     ExactArgs a;
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = raw;

@@ -361,6 +361,12 @@ const char* fenerf_last_error(void);
 int32_t fenerf_abi_version(void);
 int64_t fenerf_launch_count(void);
 
+/* Diagnostics: CUDA-event timing of the six stages of fenerf_render_forward (ray set-up, coarse field, GUARD
+ * refinement, resampling, fine field, compositing).  enable = 1 with ms_out NULL switches it on, enable = 0 off;
+ * enable = 1 with ms_out reads the six durations (ms) of the LAST call (synchronises on it).  Process-wide, not
+ * thread-safe, inactive during CUDA-graph capture. */
+int fenerf_debug_stage_times(int32_t enable, float* ms_out /* host, 6 floats */);
+
 /* Diagnostics: install a device buffer of 4 * 4096 int64 that CTA 0 of the tcgen05 point-network
  * kernel fills with (tag, clock64) pairs for its first two tile pairs, one 4096-entry lane per warp
  * role (producer, MMA issuer, epilogue X, epilogue Y); NULL (the default) disables.  Process-wide,
