@@ -18,7 +18,9 @@
 //                    trunk-head image [4 chunks][32 rows][64 k] f16 swizzled: rows 0..L-1 the
 //                    (power-of-two scaled) label map, row L the sigma weights, rest zero
 //                    rgb-head image   [4 chunks][ 8 rows][64 k] f16 swizzled: rows 0..2
-//   grid             channels-last [R][R][R][G] f32
+//   grid             channels-last [R][R][R][G] f32 (exact path, backward)
+//   grid16           the same in f16 (tcgen05 path: 64 B per voxel -- the features become fp16 MMA operands anyway;
+//                    57 MB for 32 x 96^3, which the 126 MB L2 can hold next to the weights, and half the gather stream)
 //
 // "Input chunk" slot order (the 64-wide A chunk the tcgen05 kernel builds per point):
 //   0..2 pos_hi  3..5 pos_lo  6..8 pos_hi | 16..18 dir_hi 19..21 dir_lo 22..24 dir_hi | 32..63 feat
@@ -49,7 +51,7 @@ struct FnLayout {
     size_t hid_w32[FN_MAX_HIDDEN], hid_b[FN_MAX_HIDDEN], hid_img[FN_MAX_HIDDEN];
     size_t color0_ximg;     // input-chunk image of the first colour layer
     size_t sigma_w, rgb_w, label_w, head_img, rgb_img, label_scratch;
-    size_t grid;
+    size_t grid, grid16;
     size_t total;
 };
 
@@ -95,6 +97,7 @@ static inline int fn_make_layout(const fenerf_field_desc* f, FnLayout* L) {
     L->label_scratch = take((size_t)FENERF_MAX_LABEL * (FN_H + 1) * 8);  // doubles, pack-time only
     size_t r = (size_t)f->grid_res;
     L->grid = take(f->grid_channels ? r * r * r * (size_t)f->grid_channels * 4 : 4);
+    L->grid16 = take(f->grid_channels ? r * r * r * (size_t)f->grid_channels * 2 : 4);
     L->total = off;
     return 0;
 }

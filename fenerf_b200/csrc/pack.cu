@@ -164,7 +164,7 @@ __global__ void pack_head_imgs_kernel(const float* __restrict__ lw, int L, const
 
 // ---- grid: (G, D, H, W) channel-major -> [D][H][W][G] channels-last ---------------------------
 // one block per (z, y) line: read G rows of R contiguous x, write R*G contiguous floats
-__global__ void pack_grid_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int G) {
+__global__ void pack_grid_kernel(const float* __restrict__ in, float* __restrict__ out, __half* __restrict__ out16, int R, int G) {
     extern __shared__ float line[];  // [G][R + 1]
     size_t zy = blockIdx.x;          // z * R + y
     size_t plane = (size_t)R * R * R;
@@ -174,9 +174,12 @@ __global__ void pack_grid_kernel(const float* __restrict__ in, float* __restrict
     }
     __syncthreads();
     float* dst = out + zy * R * G;
+    __half* dst16 = out16 + zy * R * G;
     for (int i = threadIdx.x; i < G * R; i += blockDim.x) {
         int x = i / G, c = i % G;
-        dst[i] = line[c * (R + 1) + x];
+        const float v = line[c * (R + 1) + x];
+        dst[i] = v;
+        dst16[i] = __float2half_rn(v);
     }
 }
 
@@ -290,7 +293,7 @@ int pack_field(const fenerf_field_desc* f, const FnLayout& L, const fenerf_field
         FN_REQUIRE(smem <= 96 * 1024, "grid_res %d too large for the transpose tile", R);
         if (smem > 48 * 1024)
             FN_CUDA_OK(cudaFuncSetAttribute(pack_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pack_grid_kernel<<<R * R, 256, smem, st>>>(p->grid, (float*)(packed + L.grid), R, G);
+        pack_grid_kernel<<<R * R, 256, smem, st>>>(p->grid, (float*)(packed + L.grid), (__half*)(packed + L.grid16), R, G);
         FN_LAUNCH_OK("pack_grid_kernel");
     }
     (void)f;
