@@ -14,7 +14,7 @@ using namespace fn;
 namespace {
 
 struct Workspace {
-    size_t stats, points_c, z_c, dirs, origins, raw_c, z_f, points_f, raw_f, guard, total;
+    size_t stats, points_c, z_c, dirs, origins, raw_c, z_f, points_f, raw_f, guard, sigma_c, total;
 };
 
 Workspace plan_workspace(const fenerf_render_desc* rd, int C) {
@@ -33,6 +33,7 @@ Workspace plan_workspace(const fenerf_render_desc* rd, int C) {
     w.points_f = take(rd->hierarchical ? pc * 3 * 4 : 4);
     w.raw_f = take(rd->hierarchical ? pc * C * 4 : 4);
     w.guard = take((n_rays + 1) * 4);
+    w.sigma_c = take(pc * 4);
     w.total = off;
     return w;
 }
@@ -65,13 +66,14 @@ void stage_mark(int i, cudaStream_t st) {
 
 int run_field(const FnLayout& L, const void* packed, const float* points, const float* dirs, const float* film,
               int batch, long long ppb, int dir_group, int lock_dirs, int precision, float* out, cudaStream_t st,
-              int sigma_only = 0) {
+              int sigma_only = 0, float* sigma_out = nullptr) {
     const unsigned char* pk = static_cast<const unsigned char*>(packed);
     if (precision == FENERF_PRECISION_EXACT)
         return siren_points_exact(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, nullptr, 0, out, st, sigma_only);
     // the tcgen05 kernel (siren_fast3.cu: third generation; its predecessors are described in DESIGN.md
     // section 5 and live in the history only)
-    return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), sigma_only, st);
+    return siren_points_fast3(L, pk, points, dirs, film, batch, ppb, dir_group, lock_dirs, out, get_fast_trace(), sigma_only, st,
+                              sigma_out);
 }
 
 }  // namespace
@@ -254,8 +256,11 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
     stage_mark(0, st);
     if (int e = ray_setup(rd, x_lin, y_lin, z_lin, cam2world, rng_perturb, points_c, z_c, dirs, origins, st)) return e;
     stage_mark(1, st);
+    // the tcgen05 pass also leaves the densities as one float per point for the resampler (which never reads the far
+    // sample, so the GUARD refinement of raw_c below does not concern that copy)
+    float* sigma_c = (rd->hierarchical && rd->precision != FENERF_PRECISION_EXACT) ? (float*)(ws + w.sigma_c) : nullptr;
     if (int e = run_field(L, packed, points_c, dirs, film, rd->batch, ppb, rd->num_steps, rd->lock_view_dependence,
-                          rd->precision, raw_c, st)) return e;
+                          rd->precision, raw_c, st, 0, sigma_c)) return e;
     stage_mark(2, st);
     if (rd->precision == FENERF_PRECISION_GUARD) {
         float tau = rd->guard_tau > 0.f ? rd->guard_tau : 1.5e-3f;
@@ -267,7 +272,7 @@ int fenerf_render_forward(const fenerf_render_desc* rd, const fenerf_field_desc*
     stage_mark(3, st);
     if (rd->hierarchical) {
         if (int e = resample(rd, C, raw_c, z_c, dirs, origins, noise_c, rng_u, z_f, points_f, (long long*)inds_dbg, st,
-                             /*sort_fine=*/1)) return e;
+                             /*sort_fine=*/1, sigma_c)) return e;
         stage_mark(4, st);
         if (int e = run_field(L, packed, points_f, dirs, film, rd->batch, ppb, rd->num_steps, rd->lock_view_dependence,
                               rd->precision, raw_f, st)) return e;

@@ -89,7 +89,7 @@ void set_fast_trace(long long* buf);
 long long* get_fast_trace();
 int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
-                       long long* trace, int sigma_only, cudaStream_t st);
+                       long long* trace, int sigma_only, cudaStream_t st, float* sigma_out = nullptr);
 int guard_refine(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                  const float* film, int batch, long long rays_per_batch, int num_steps, int lock_dirs, float tau,
                  const float* noise_far, long long noise_stride, float noise_std,
@@ -101,7 +101,7 @@ int ray_setup(const fenerf_render_desc* rd, const float* x_lin, const float* y_l
               float* origins, cudaStream_t st);
 int resample(const fenerf_render_desc* rd, int C, const float* raw, const float* z, const float* dirs,
              const float* origins, const float* noise, const float* u, float* z_fine, float* pts_fine,
-             long long* inds, cudaStream_t st, int sort_fine = 0);
+             long long* inds, cudaStream_t st, int sort_fine = 0, const float* sigma_compact = nullptr);
 int composite_sorted(const fenerf_render_desc* rd, int C, const float* raw_c, const float* z_c, const float* raw_f,
                      const float* z_f, const float* noise, float* pixels, float* depth, float* wsum, float* weights,
                      cudaStream_t st);

@@ -246,13 +246,18 @@ __global__ void __launch_bounds__(kRaysPerBlock * 32) composite_kernel(Composite
 // in registers across its samples.  A warp's 32 rays write 32 consecutive pixels of every channel plane:
 // coalesced NCHW stores.  No shared memory, no shuffles: ~50x fewer instructions than the warp-per-ray kernel
 // above (which stays as the general entry: unsorted inputs, merge-order output).
-template <int CMAX>
+// TPR threads share a ray (1 for the 4-channel field; 4 for the 22-channel one: each owns every 4th channel, all of
+// them walk the merge and the transmittance redundantly -- it is the channel sums and their loads that are split).
+template <int CMAX, int TPR>
 __global__ void __launch_bounds__(128) composite_ray_kernel(CompositeArgs A) {
     const int n = A.n_samples, S = A.S, C = A.C;
     const bool hier = (n != S);
     const bool pad = (A.fill_mode == FENERF_FILL_SEG_PADDING_BACKGROUND || A.fill_mode == FENERF_FILL_EVAL_SEG_PADDING_BACKGROUND);
-    for (long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x; ray < A.n_rays;
-         ray += (long long)gridDim.x * blockDim.x) {
+    const int q = TPR == 1 ? 0 : (int)(threadIdx.x % TPR);
+    const long long n_threads = A.n_rays * TPR;
+    for (long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x; gt < n_threads;
+         gt += (long long)gridDim.x * blockDim.x) {
+        const long long ray = gt / TPR;
         const long long base = ray * S;
         const float* zf = hier ? A.z_f + base : nullptr;
         const float* zc = A.z_c + base;
@@ -263,7 +268,6 @@ __global__ void __launch_bounds__(128) composite_ray_kernel(CompositeArgs A) {
         for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
         float T = 1.f, wsum = 0.f, depth = 0.f;
         int i_f = 0, i_c = 0;
-        // current sample (the one whose interval ends at the next sample's depth)
         float z_cur;
         const float* r_cur;
         {
@@ -292,16 +296,16 @@ __global__ void __launch_bounds__(128) composite_ray_kernel(CompositeArgs A) {
             const float wj = __fmul_rn(alpha, T);
             T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
             wsum = __fadd_rn(wsum, wj);
-            if (A.weights) A.weights[ray * n + j] = wj;
+            if (A.weights && q == 0) A.weights[ray * n + j] = wj;
             if (j < n - 1 || !A.last_back) {
                 depth = fmaf(wj, z_cur, depth);
-                if (CMAX == 3) {
+                if (CMAX == 3 && TPR == 1) {
                     const float4 v = *reinterpret_cast<const float4*>(r_cur);      // C == 4: one 16-byte load per sample
                     acc[0] = fmaf(wj, v.x, acc[0]); acc[1] = fmaf(wj, v.y, acc[1]); acc[2] = fmaf(wj, v.z, acc[2]);
                 } else {
 #pragma unroll
                     for (int c = 0; c < CMAX; ++c)
-                        if (c < C - 1) acc[c] = fmaf(wj, r_cur[c], acc[c]);
+                        if (q + TPR * c < C - 1) acc[c] = fmaf(wj, r_cur[q + TPR * c], acc[c]);
                 }
             } else {
                 w_last = wj;      // last_back: the far sample's weight absorbs 1 - weights_sum (volumetric_rendering.py:41-42)
@@ -310,55 +314,60 @@ __global__ void __launch_bounds__(128) composite_ray_kernel(CompositeArgs A) {
         }
         if (A.last_back) {
             const float wl = __fadd_rn(w_last, __fsub_rn(1.f, wsum));
-            if (A.weights) A.weights[ray * n + n - 1] = wl;
+            if (A.weights && q == 0) A.weights[ray * n + n - 1] = wl;
             depth = fmaf(wl, z_cur, depth);
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
-                if (c < C - 1) acc[c] = fmaf(wl, r_cur[c], acc[c]);
+                if (q + TPR * c < C - 1) acc[c] = fmaf(wl, r_cur[q + TPR * c], acc[c]);
         }
-        if (A.depth) A.depth[ray] = depth;
-        if (A.wsum) A.wsum[ray] = wsum;
+        if (q == 0) {
+            if (A.depth) A.depth[ray] = depth;
+            if (A.wsum) A.wsum[ray] = wsum;
+        }
         const bool empty = wsum < 0.9f;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-            if (c >= C - 1) continue;
+            const int ch = q + TPR * c;
+            if (ch >= C - 1) continue;
             float v = acc[c];
             if (A.white_back) v = __fsub_rn(__fadd_rn(v, 1.f), wsum);
             if (A.black_back) v = __fadd_rn(v, __fmul_rn(__fsub_rn(1.f, wsum), -1.f));
             if (pad) { if (empty && A.fill_color >= 0.f) v = A.fill_color; }
-            else if (A.fill_mode == FENERF_FILL_DEBUG || A.fill_mode == FENERF_FILL_WEIGHT_DEBUG) { if (empty) v = (c == 0) ? 1.f : 0.f; }
+            else if (A.fill_mode == FENERF_FILL_DEBUG || A.fill_mode == FENERF_FILL_WEIGHT_DEBUG) { if (empty) v = (ch == 0) ? 1.f : 0.f; }
             else if (A.fill_mode == FENERF_FILL_EVAL_WHITE_BACK) { if (empty) v = 1.f; }
             acc[c] = v;
         }
+        const unsigned rpb = (unsigned)A.rays_per_batch;
+        const long long b = (unsigned)ray / rpb, p = (unsigned)ray % rpb;
+        const float bgv = (empty && A.fill_color >= 0.f) ? 1.f : 0.f;      // the padded background channel
+        float bg_out = bgv;
         if (A.softmax_label) {
+            // softmax over the channels before the last three (generators.py:97-100); with a padded background channel
+            // it runs over [background, labels]
             const int n_seg = A.C_img - 3 - (pad ? 1 : 0);
-            // with a padded background channel the reference's softmax runs over [background, labels]; background value:
-            const float bgv = (empty && A.fill_color >= 0.f) ? 1.f : 0.f;
+            const unsigned grp = __activemask();      // whole groups of TPR lanes are in or out of the loop together
             float m = pad ? bgv : -INFINITY;
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c) if (c < n_seg) m = fmaxf(m, acc[c]);
-            float sum = pad ? expf(__fsub_rn(bgv, m)) : 0.f;
+            for (int c = 0; c < CMAX; ++c) if (q + TPR * c < n_seg) m = fmaxf(m, acc[c]);
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c) if (c < n_seg) { acc[c] = expf(__fsub_rn(acc[c], m)); sum += acc[c]; }
+            for (int off = 1; off < TPR; off <<= 1) m = fmaxf(m, __shfl_xor_sync(grp, m, off));
+            float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c) if (c < n_seg) acc[c] = __fdiv_rn(acc[c], sum);
-            if (pad) {
-                const unsigned rpb = (unsigned)A.rays_per_batch;
-                const long long b = (unsigned)ray / rpb, p = (unsigned)ray % rpb;
-                A.pixels[(b * A.C_img) * A.rays_per_batch + p] = __fsub_rn(__fmul_rn(__fdiv_rn(expf(__fsub_rn(bgv, m)), sum), 2.f), 1.f);
-            }
-        } else if (pad) {
-            const unsigned rpb = (unsigned)A.rays_per_batch;
-            const long long b = (unsigned)ray / rpb, p = (unsigned)ray % rpb;
-            A.pixels[(b * A.C_img) * A.rays_per_batch + p] = ((empty && A.fill_color >= 0.f) ? 1.f : 0.f) * 2.f - 1.f;
+            for (int c = 0; c < CMAX; ++c) if (q + TPR * c < n_seg) { acc[c] = expf(__fsub_rn(acc[c], m)); sum += acc[c]; }
+#pragma unroll
+            for (int off = 1; off < TPR; off <<= 1) sum += __shfl_xor_sync(grp, sum, off);
+            const float ebg = pad ? expf(__fsub_rn(bgv, m)) : 0.f;
+            sum += ebg;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) if (q + TPR * c < n_seg) acc[c] = __fdiv_rn(acc[c], sum);
+            bg_out = __fdiv_rn(ebg, sum);
         }
-        {
-            const unsigned rpb = (unsigned)A.rays_per_batch;
-            const long long b = (unsigned)ray / rpb, p = (unsigned)ray % rpb;
-            const int shift = pad ? 1 : 0;
+        if (pad && q == 0) A.pixels[(b * A.C_img) * A.rays_per_batch + p] = __fsub_rn(__fmul_rn(bg_out, 2.f), 1.f);
+        const int shift = pad ? 1 : 0;
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-                if (c < C - 1) A.pixels[(b * A.C_img + c + shift) * A.rays_per_batch + p] = __fsub_rn(__fmul_rn(acc[c], 2.f), 1.f);
+        for (int c = 0; c < CMAX; ++c) {
+            const int ch = q + TPR * c;
+            if (ch < C - 1) A.pixels[(b * A.C_img + ch + shift) * A.rays_per_batch + p] = __fsub_rn(__fmul_rn(acc[c], 2.f), 1.f);
         }
     }
 }
@@ -388,12 +397,13 @@ int composite_sorted(const fenerf_render_desc* rd, int C, const float* raw_c, co
     A.n_pad = 0; A.warp_floats = 0;
     if (rd->hierarchical) FN_REQUIRE(raw_f && z_f, "hierarchical render needs raw_fine and z_fine");
     const int threads = 128;
-    long long want = (A.n_rays + threads - 1) / threads;
+    const int tpr = C > 8 ? 4 : 1;
+    long long want = (A.n_rays * tpr + threads - 1) / threads;
     long long cap = (long long)num_sms() * 16;
     const int blocks = (int)(want < cap ? want : cap);
-    if (C == 4 && (((uintptr_t)raw_c | (uintptr_t)raw_f) & 15) == 0) composite_ray_kernel<3><<<blocks, threads, 0, st>>>(A);
-    else if (C <= 8) composite_ray_kernel<7><<<blocks, threads, 0, st>>>(A);
-    else composite_ray_kernel<31><<<blocks, threads, 0, st>>>(A);
+    if (C == 4 && (((uintptr_t)raw_c | (uintptr_t)raw_f) & 15) == 0) composite_ray_kernel<3, 1><<<blocks, threads, 0, st>>>(A);
+    else if (C <= 8) composite_ray_kernel<7, 1><<<blocks, threads, 0, st>>>(A);
+    else composite_ray_kernel<8, 4><<<blocks, threads, 0, st>>>(A);
     FN_LAUNCH_OK("composite_ray_kernel");
     return 0;
 }

@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(128)
 resample_ray_kernel(long long n_rays, long long rays_per_batch, int S, int C, int clamp_mode, float noise_std,
                     const float* __restrict__ raw, const float* __restrict__ z_vals, const float* __restrict__ dirs,
                     const float* __restrict__ origins, const float* __restrict__ noise, const float* __restrict__ u,
-                    float* __restrict__ z_fine, float* __restrict__ pts_fine, long long* __restrict__ inds, int sort_fine) {
+                    float* __restrict__ z_fine, float* __restrict__ pts_fine, long long* __restrict__ inds, int sort_fine,
+                    const float* __restrict__ sigma_compact) {
     // per-thread arrays live in shared memory as [index][thread]: whatever index a lane uses, its bank is its lane id,
     // so the data-dependent accesses of the binary search and the insertion sort never conflict (thread-local arrays
     // would be 768 B of local memory per thread: ~340 KB per SM, thrashing the L1).  The block's 128 rays are
@@ -58,13 +59,16 @@ resample_ray_kernel(long long n_rays, long long rays_per_batch, int S, int C, in
             const int r = i / S, ss = i - r * S;
             z_[ss * nt + r] = z_vals[ray0 * S + i];
             zf_[ss * nt + r] = u[ray0 * S + i];
+            // densities: from the point network's compact per-point copy when the caller has one (coalesced), else
+            // channel C-1 of the raw rows (a 4-byte read per 4C-byte row)
+            if (sigma_compact) cdf_[ss * nt + r] = sigma_compact[ray0 * S + i];
         }
         __syncthreads();
         if (ray < n_rays) {
             // interior weights + 2e-5 (generators.py:63, volumetric_rendering.py:273); the far sample is never read
             float T = 1.f, total = 0.f;
             for (int s = 0; s < S - 1; ++s) {
-                float sig = raw[(base + s) * C + (C - 1)];
+                float sig = sigma_compact ? cdf(s) : raw[(base + s) * C + (C - 1)];      // (slot s is overwritten only by s-1)
                 if (noise) sig = __fadd_rn(sig, __fmul_rn(noise[base + s], noise_std));
                 const float delta = __fsub_rn(z(s + 1), z(s));
                 const float act = clamp_mode == FENERF_CLAMP_RELU ? fmaxf(sig, 0.f) : softplus_torch(sig);
@@ -135,7 +139,7 @@ resample_ray_kernel(long long n_rays, long long rays_per_batch, int S, int C, in
 
 int resample(const fenerf_render_desc* rd, int C, const float* raw, const float* z, const float* dirs,
              const float* origins, const float* noise, const float* u, float* z_fine, float* pts_fine,
-             long long* inds, cudaStream_t st, int sort_fine) {
+             long long* inds, cudaStream_t st, int sort_fine, const float* sigma_compact) {
     FN_REQUIRE(rd->num_steps >= 3 && rd->num_steps <= kMaxS, "num_steps %d outside [3, %d] for resampling",
                rd->num_steps, kMaxS);
     long long rpb = (long long)rd->img_h * rd->img_w;
@@ -148,7 +152,7 @@ int resample(const fenerf_render_desc* rd, int C, const float* raw, const float*
     static std::atomic<int> smem_set[kMaxDevices];
     if (smem > 48 * 1024) FN_CUDA_OK(ensure_dynamic_smem(resample_ray_kernel, smem_set, (int)smem));
     resample_ray_kernel<<<blocks, 128, smem, st>>>(n_rays, rpb, rd->num_steps, C, rd->clamp_mode, rd->noise_std, raw, z, dirs, origins,
-                                                noise, u, z_fine, pts_fine, inds, sort_fine);
+                                                noise, u, z_fine, pts_fine, inds, sort_fine, sigma_compact);
     FN_LAUNCH_OK("resample_ray_kernel");
     return 0;
 }

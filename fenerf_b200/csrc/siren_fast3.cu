@@ -92,6 +92,7 @@ struct Fast3Args {
     const float* dirs;
     const float* film;
     float* out;
+    float* sigma_out;      // optional compact copy of the density channel, one float per point (the resampler's input)
     long long ppb, tiles_per_batch, n_tiles;
     int dir_group, lock_dirs;
     int debug_short_loads;
@@ -524,6 +525,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                     if (o + 1 == L.label_dim) sig_keep = __uint_as_float(r[o + 1]) + __ldg(sigma_w + FN_H);
                                 }
                                 if (a.sigma_only) orow[C - 1] = sig_keep;
+                                if (a.sigma_out) a.sigma_out[flat] = sig_keep;
                             }
                         } else {
                             uint32_t r[8];
@@ -531,6 +533,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             tc_wait_ld();
                             sig_keep = __uint_as_float(r[0]) + __ldg(sigma_w + FN_H);
                             if (valid && a.sigma_only) a.out[flat * C + (C - 1)] = sig_keep;
+                            if (valid && a.sigma_out) a.sigma_out[flat] = sig_keep;
                         }
                     } else {
                         uint32_t r[8];
@@ -656,7 +659,7 @@ long long* get_fast_trace() { return g_trace; }
 
 int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const float* points, const float* dirs,
                        const float* film, int batch, long long ppb, int dir_group, int lock_dirs, float* out,
-                       long long* trace, int sigma_only, cudaStream_t st) {
+                       long long* trace, int sigma_only, cudaStream_t st, float* sigma_out) {
     static_assert(sizeof(Fast3Args) <= 4000, "kernel parameter block too large");
     static_assert(SMEM_TOTAL <= 232448, "one CTA per SM: 227 KB of shared memory");
     FN_REQUIRE(L.trunk_hidden >= 1 && L.n_hidden - L.trunk_hidden >= 1, "field needs >= 2 trunk and >= 1 colour layers");
@@ -665,7 +668,7 @@ int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const flo
     memset(&a, 0, sizeof(a));
     FN_REQUIRE(build_program(L, a, sigma_only != 0), "field too deep for the stage program");
     a.sigma_only = sigma_only ? 1 : 0;
-    a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out;
+    a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out; a.sigma_out = sigma_out;
     a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
     a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs; a.trace = trace;
 #ifdef FENERF_DEBUG_SHORT_LOADS
