@@ -179,8 +179,9 @@ def cpu_faces_per_sec(model, steps, warmup, budget_s=200.0):
         oracle.render(gen.siren, film, md)
     dt = (time.perf_counter() - t0) / steps
     frac = (r / IMG) ** 2
-    sample = "%d step(s) of %dx%d rays (%.3g of one cfg2 face, B=1, %d+%d samples/ray), oracle port, fp32, %d threads (best of a thread-count probe on %d host cores)" % (
-        steps, r, r, frac, STEPS_PER_RAY, STEPS_PER_RAY, cores, avail)
+    sample = ("%d step(s) of %dx%d rays (%.3g of one cfg2 face, B=1, %d+%d samples/ray), oracle port, fp32, %d threads (best of a "
+              "thread-count probe on %d host cores); the port takes 0.93-1.16x the live reference's time on the build container "
+              "(profiles/r02_port_vs_reference.txt)" % (steps, r, r, frac, STEPS_PER_RAY, STEPS_PER_RAY, cores, avail))
     return frac / dt, sample, cores
 
 
