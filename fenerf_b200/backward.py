@@ -11,10 +11,10 @@ forward   ONE ``fenerf_render_forward`` call into a private workspace -- the sam
 backward  ``fenerf_composite_backward`` (d pixels -> d raw outputs, one warp per ray), then the point
           network layer by layer, recomputing activations chunk by chunk (nothing but the workspace
           survives from the forward):
-            recompute   z = a W^T (library GEMM, fp16 operands / fp32 out) -> ``fenerf_film_forward_stash``
-                        writes a = sin(f z + p) and the gate f cos(f z + p) as fp16
-            backward    ``fenerf_gate_backward`` dZ = dA * gate (+ per-image column sums), dA' = dZ W and the
-                        per-image dW_b = dZ^T a (library GEMMs)
+            recompute   ``fenerf_gemm_nt_film``: z = a W^T on tcgen05 with the epilogue fused -- a = sin(f z + p) and
+                        the gate f cos(f z + p) leave as fp16, z never does
+            backward    ``fenerf_gate_backward`` dZ = dA * gate (+ per-image column sums), dA' = dZ W
+                        (``fenerf_gemm_nt_f16``) and the per-image dW_b = dZ^T a (``fenerf_gemm_tn_f16``, split-K)
           FiLM gradients need no further pass over the points:  dp = db_b / f,
           df = (sum_k W[f,k] dW_b[f,k]) / f + b dp   (u = f z + p, z = W a + b).
           Heads, the pre-multiplied label chain and the grid (``fenerf_grid_scatter_add``) close the chain.
@@ -22,9 +22,10 @@ Gradients flow to the FiLM table (and through torch's autograd into the mapping 
 frequency offsets) and to every field parameter.  The fp16 gradient stream is scaled by a power of two
 taken from max|d raw| on the device (no host sync) and unscaled at the end.
 
-The 256-wide products are plain GEMMs and go to the library (cuBLAS via ``torch.mm(out_dtype=)``); the
-tcgen05 formulation of this backward (transposed weight images through the forward kernel's own ring, gate
-multiply in its epilogue, split-K dW in TMEM) is described in DESIGN.md and not built.
+The three 256-wide products per layer run on tcgen05 (csrc/gemm5.cu: ``fenerf_gemm_nt_film`` -- the recompute with its FiLM
+epilogue fused, ``fenerf_gemm_nt_f16`` for dA' = dZ W, ``fenerf_gemm_tn_f16`` split-K for the per-image dW); only the narrow
+products (heads, the 3 / 35-wide inputs) go to the library.  ``FENERF_B200_BWD_GEMM=cublas`` switches the wide ones back
+(A/B timing); ``precision='exact'`` always uses fp32 library GEMMs.
 """
 import ctypes as C
 
@@ -32,7 +33,12 @@ import torch
 
 from . import _lib, ops, packing
 
+import os
+
 CHUNK_POINTS = 1 << 19
+#: the 256-wide products: 'tcgen05' = csrc/gemm5.cu (default), 'cublas' = torch.mm / bmm (kept for A/B timing and as the
+#: fp32 path of precision='exact')
+BWD_GEMM = os.environ.get("FENERF_B200_BWD_GEMM", "tcgen05")
 
 
 def _ptr(t):
@@ -151,11 +157,15 @@ class _FieldBackward:
         # fp16 / fp32 weight views for the GEMMs
         fw = self.fw
         self.W0 = fw.trunk[0][0].detach().float().contiguous()                    # (256, 3)
+        self.own_gemm = (not exact) and BWD_GEMM == "tcgen05"
         self.Wh16 = [None] + [w.detach().to(self.dt).contiguous() for w, _ in fw.trunk[1:]]
         wc0 = fw.color[0][0].detach().float()
         self.Wc0x_narrow = wc0[:, :self.kx].contiguous()                          # (256, 3 + G) fp32
         self.Wc16 = [wc0[:, self.kx:].to(self.dt).contiguous()] + [w.detach().to(self.dt).contiguous() for w, _ in fw.color[1:]]
         self.Wfeat16 = wc0[:, 3:self.kx].to(self.dt).contiguous() if G else None       # (256, G)
+        # dA' = dZ W on the tcgen05 NT kernel wants the transposed weights as its (N, K) operand
+        self.WhT16 = [None] + [w.t().contiguous() for w in self.Wh16[1:]] if self.own_gemm else None
+        self.WcT16 = [w.t().contiguous() for w in self.Wc16] if self.own_gemm else None
         L = self.spec.label_dim
         self.L = L
         heads = torch.zeros((32, 256), dtype=torch.float32, device=dev)
@@ -219,16 +229,21 @@ class _FieldBackward:
             _lib.check(lib.fenerf_extras_gather(C.byref(self.packed.desc), self.packed.ptr, points.data_ptr(), dirs.data_ptr(),
                                                 P, ppb, dir_group, int(bool(lock_dirs)), extras.data_ptr(), st))
             A, Gt = [None] * self.n_film, [None] * self.n_film
+            own = self.own_gemm
             A[0], Gt[0] = self._stash(None, 0, b0, P, ppb, xin=x, wx=self.W0)
             for l in range(1, T):
-                z = _mm32(A[l - 1], self.Wh16[l].t())
-                A[l], Gt[l] = self._stash(z, l, b0, P, ppb)
-            z = _mm32(A[T - 1], self.Wc16[0].t())
+                if own:     # z = a W^T with the FiLM epilogue fused: z never leaves the SM
+                    A[l], Gt[l] = ops.gemm_nt_film(A[l - 1], self.Wh16[l], self.bias[l], self.film, b0, l, ppb)
+                else:
+                    A[l], Gt[l] = self._stash(_mm32(A[l - 1], self.Wh16[l].t()), l, b0, P, ppb)
+            z = ops.gemm_nt(A[T - 1], self.Wc16[0]) if own else _mm32(A[T - 1], self.Wc16[0].t())
             A[T], Gt[T] = self._stash(z, T, b0, P, ppb, xin=extras, wx=self.Wc0x_narrow)
-            for j in range(1, Cn):
-                z = _mm32(A[T + j - 1], self.Wc16[j].t())
-                A[T + j], Gt[T + j] = self._stash(z, T + j, b0, P, ppb)
             del z
+            for j in range(1, Cn):
+                if own:
+                    A[T + j], Gt[T + j] = ops.gemm_nt_film(A[T + j - 1], self.Wc16[j], self.bias[T + j], self.film, b0, T + j, ppb)
+                else:
+                    A[T + j], Gt[T + j] = self._stash(_mm32(A[T + j - 1], self.Wc16[j].t()), T + j, b0, P, ppb)
             # ---- head gradients ----
             dH = torch.empty((P, 32), dtype=self.dt, device=dev)
             dRGB = torch.empty((P, 8), dtype=self.dt, device=dev)
@@ -246,7 +261,7 @@ class _FieldBackward:
                 self._gate(dA, Gt[idx], idx, b0, b1, P, ppb)                   # dA is dZ now
                 a_in = A[idx - 1]
                 dz3 = dA.view(k, ppb, 256).transpose(1, 2)
-                self.dW_b[idx][b0:b1] += _bmm32(dz3, a_in.view(k, ppb, 256))
+                self.dW_b[idx][b0:b1] += ops.gemm_tn(dA, a_in, k, ppb) if own else _bmm32(dz3, a_in.view(k, ppb, 256))
                 if j == 0:
                     e16 = torch.zeros((P, self.kx_pad), dtype=self.dt, device=dev)
                     e16[:, :self.kx] = extras
@@ -255,14 +270,18 @@ class _FieldBackward:
                         d_feat = torch.mm(dA, self.Wfeat16).contiguous()       # (P, G) fp16
                         _lib.check(lib.fenerf_grid_scatter_add(C.byref(self.packed.desc), points.data_ptr(), d_feat.data_ptr(),
                                                                d_feat.shape[1], P, self.grid_grad_cl.data_ptr(), self.dtc, st))
-                dA = torch.mm(dA, self.Wc16[j])
+                dA = ops.gemm_nt(dA, self.WcT16[j], torch.float16) if own else torch.mm(dA, self.Wc16[j])
                 A[idx], Gt[idx] = None, None
             # ---- trunk: colour-branch gradient + sigma / label heads ----
             dA += torch.mm(dH.float(), self.Wheads32)
             for l in range(T - 1, 0, -1):
                 self._gate(dA, Gt[l], l, b0, b1, P, ppb)
-                self.dW_b[l][b0:b1] += _bmm32(dA.view(k, ppb, 256).transpose(1, 2), A[l - 1].view(k, ppb, 256))
-                dA = torch.mm(dA, self.Wh16[l])
+                if own:
+                    self.dW_b[l][b0:b1] += ops.gemm_tn(dA, A[l - 1], k, ppb)
+                    dA = ops.gemm_nt(dA, self.WhT16[l], torch.float16)
+                else:
+                    self.dW_b[l][b0:b1] += _bmm32(dA.view(k, ppb, 256).transpose(1, 2), A[l - 1].view(k, ppb, 256))
+                    dA = torch.mm(dA, self.Wh16[l])
                 A[l], Gt[l] = None, None
             self._gate(dA, Gt[0], 0, b0, b1, P, ppb)
             x16 = torch.zeros((P, 8), dtype=self.dt, device=dev)

@@ -109,6 +109,10 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
               const float* z_f, const float* noise, float* pixels, float* depth, float* wsum, float* weights,
               int32_t* sort_idx, cudaStream_t st);
 
+// gemm5.cu
+int gemm_nt(const void* A, const void* B, long long M, float* c32, void* c16, void* a_out, void* gate_out, const float* bias,
+            const float* film, long long film_stride, long long ppb, cudaStream_t st);
+int gemm_tn(const void* X, const void* Y, int batch, long long ppb, int slices, float* partial, cudaStream_t st);
 // mapping.cu
 int mapping_film(const float* const* w, const float* const* b, const float* z, int B, int z_dim, int n_layers, int layer0,
                  int n_film_total, const float* avg_f, const float* avg_p, float psi, float* h_scratch, float* film,

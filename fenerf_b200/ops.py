@@ -373,3 +373,45 @@ def mapping_film(net, z, film, first_layer, n_layers, avg=None, psi=1.0):
             C.byref(p), _chk(z, "z", device), bsz, n_layers, first_layer, film.shape[1], _chk(af, "avg_frequencies", device),
             _chk(ap, "avg_phase_shifts", device), float(psi), h.data_ptr(), _chk(film, "film", device), _stream(device)))
     return film
+
+
+# --------------------------------------------------------------------------------------------
+# tcgen05 GEMMs of the backward (csrc/gemm5.cu)
+# --------------------------------------------------------------------------------------------
+def gemm_nt(a16, b16, out_dtype=torch.float32):
+    """(M, 256) fp16 . (256, 256)^T fp16 -> (M, 256) fp32 or fp16 (fenerf_gemm_nt_f16)."""
+    dev = a16.device
+    m = a16.shape[0]
+    out = torch.empty((m, 256), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().fenerf_gemm_nt_f16(
+            _chk(a16, "A", dev, torch.float16), _chk(b16, "B", dev, torch.float16), m,
+            out.data_ptr() if out_dtype == torch.float32 else 0, out.data_ptr() if out_dtype == torch.float16 else 0, _stream(dev)))
+    return out
+
+
+def gemm_nt_film(a16, w16, bias, film, b0, layer, ppb):
+    """One FiLM layer's recompute with the epilogue fused (fenerf_gemm_nt_film): -> (a, gate), both (M, 256) fp16."""
+    dev = a16.device
+    m = a16.shape[0]
+    a_out = torch.empty((m, 256), dtype=torch.float16, device=dev)
+    g_out = torch.empty((m, 256), dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().fenerf_gemm_nt_film(
+            _chk(a16, "A", dev, torch.float16), _chk(w16, "W", dev, torch.float16), m, _chk(bias, "bias", dev),
+            film[b0, layer].data_ptr(), film.stride(0), ppb, a_out.data_ptr(), g_out.data_ptr(), _stream(dev)))
+    return a_out, g_out
+
+
+def gemm_tn(x16, y16, batch, ppb, slices=None):
+    """Per image b: X_b^T Y_b with X, Y (batch * ppb, 256) fp16 -> (batch, 256, 256) fp32 (fenerf_gemm_tn_f16; the
+    split-K partials of the CTAs are summed here)."""
+    dev = x16.device
+    if slices is None:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        slices = max(1, min((ppb + 63) // 64, (sms + batch - 1) // batch))
+    partial = torch.empty((batch, slices, 256, 256), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().fenerf_gemm_tn_f16(_chk(x16, "X", dev, torch.float16), _chk(y16, "Y", dev, torch.float16), batch,
+                                                 ppb, slices, partial.data_ptr(), _stream(dev)))
+    return partial.sum(1) if slices > 1 else partial[:, 0]

@@ -565,6 +565,41 @@ def test_fused_mapping_network_matches_the_modules(name, batch):
     assert film.requires_grad
 
 
+@pytest.mark.parametrize("m", [128, 1000, 128 * 149 + 17])
+def test_tcgen05_gemm_nt_against_fp32_matmul(m):
+    g = torch.Generator(device=DEV).manual_seed(m)
+    a = (torch.randn(m, 256, device=DEV, generator=g) * 0.5).half()
+    w = (torch.randn(256, 256, device=DEV, generator=g) * 0.1).half()
+    want = a.float() @ w.float().t()
+    got32 = ops.gemm_nt(a, w, torch.float32)
+    got16 = ops.gemm_nt(a, w, torch.float16)
+    scale = want.abs().max()
+    assert (got32 - want).abs().max() <= 2e-5 * scale, float((got32 - want).abs().max() / scale)
+    assert (got16.float() - want).abs().max() <= 1e-3 * scale
+    # the fused FiLM epilogue
+    B, ppb = 2, (m + 1) // 2
+    mm = B * ppb
+    a2 = (torch.randn(mm, 256, device=DEV, generator=g) * 0.5).half()
+    film = torch.stack([torch.rand(B, 3, 256, device=DEV, generator=g) * 40 + 10, torch.randn(B, 3, 256, device=DEV, generator=g)], 2).contiguous()
+    bias = torch.randn(256, device=DEV, generator=g) * 0.1
+    act, gate = ops.gemm_nt_film(a2, w, bias, film, 0, 1, ppb)
+    z = (a2.float() @ w.float().t() + bias).reshape(B, ppb, 256)
+    u = film[:, 1, 0].unsqueeze(1) * z + film[:, 1, 1].unsqueeze(1)
+    assert (act.float().reshape(B, ppb, 256) - torch.sin(u)).abs().max() <= 2e-3
+    assert (gate.float().reshape(B, ppb, 256) - film[:, 1, 0].unsqueeze(1) * torch.cos(u)).abs().max() <= 2e-3 * 50
+
+
+@pytest.mark.parametrize("batch,ppb,slices", [(1, 64, 1), (2, 200, 3), (3, 4096 * 3 + 5, None)])
+def test_tcgen05_gemm_tn_against_fp32_bmm(batch, ppb, slices):
+    g = torch.Generator(device=DEV).manual_seed(ppb)
+    x = (torch.randn(batch * ppb, 256, device=DEV, generator=g) * 0.5).half()
+    y = (torch.randn(batch * ppb, 256, device=DEV, generator=g) * 0.5).half()
+    want = torch.bmm(x.float().reshape(batch, ppb, 256).transpose(1, 2), y.float().reshape(batch, ppb, 256))
+    got = ops.gemm_tn(x, y, batch, ppb, slices)
+    scale = want.abs().max()
+    assert (got - want).abs().max() <= 5e-5 * scale, float((got - want).abs().max() / scale)
+
+
 def test_frame_consumers_match_the_reference_loops():
     """mask2color (train_double_latent_semantic.py:66-72) and save_image's quantisation (fid_evaluation.py:149)."""
     from fenerf_b200 import frames
