@@ -313,10 +313,11 @@ int fenerf_frames_to_u8(const float* frames, int32_t batch, int32_t channels, in
 }
 
 // ---- backward ---------------------------------------------------------------
-int fenerf_gemm_nt_f16(const void* A, const void* B, int64_t M, float* c_f32, void* c_f16, void* stream) {
+int fenerf_gemm_nt_f16(const void* A, const void* B, int64_t M, float* c_f32, void* c_f16, const void* gate_mul, void* stream) {
     FN_REQUIRE(A && B && M >= 0 && ((c_f32 != nullptr) != (c_f16 != nullptr)), "bad argument (exactly one of c_f32 / c_f16)");
-    FN_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)c_f32 | (uintptr_t)c_f16) & 15) == 0, "operands must be 16-byte aligned");
-    return gemm_nt(A, B, M, c_f32, c_f16, nullptr, nullptr, nullptr, nullptr, 0, 1, (cudaStream_t)stream);
+    FN_REQUIRE(!gate_mul || c_f16, "gate_mul goes with the fp16 output");
+    FN_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)c_f32 | (uintptr_t)c_f16 | (uintptr_t)gate_mul) & 15) == 0, "operands must be 16-byte aligned");
+    return gemm_nt(A, B, M, c_f32, c_f16, nullptr, nullptr, nullptr, nullptr, 0, 1, (cudaStream_t)stream, gate_mul);
 }
 
 int fenerf_gemm_nt_film(const void* A, const void* W, int64_t M, const float* bias, const float* film_layer,
@@ -328,10 +329,10 @@ int fenerf_gemm_nt_film(const void* A, const void* W, int64_t M, const float* bi
 }
 
 int fenerf_gemm_tn_f16(const void* X, const void* Y, int32_t batch, int64_t points_per_batch, int32_t slices, float* partial,
-                       void* stream) {
+                       float* colsum, void* stream) {
     FN_REQUIRE(X && Y && partial && batch >= 1 && points_per_batch >= 1 && slices >= 1, "bad argument");
     FN_REQUIRE((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)partial) & 15) == 0, "operands must be 16-byte aligned");
-    return gemm_tn(X, Y, batch, points_per_batch, slices, partial, (cudaStream_t)stream);
+    return gemm_tn(X, Y, batch, points_per_batch, slices, partial, (cudaStream_t)stream, colsum);
 }
 
 int fenerf_composite_backward(const fenerf_render_desc* rd, int32_t out_dim, const float* raw_coarse, const float* z_coarse,

@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(256) film_forward_stash_kernel(
             const float fr = __ldg(fl + f0 + i), ph = __ldg(fl + FN_H + f0 + i);
             const float u = fmaf(fr, acc[i] + __ldg(bias + f0 + i), ph);
             float sn, cs;
-            sincosf(u, &sn, &cs);
+            if (sizeof(T) == 2) __sincosf(u, &sn, &cs);     // fp16 streams: the MUFU pair is far inside their rounding
+            else sincosf(u, &sn, &cs);
             av.set(i, sn);
             gv.set(i, fr * cs);
         }

@@ -111,8 +111,9 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
 
 // gemm5.cu
 int gemm_nt(const void* A, const void* B, long long M, float* c32, void* c16, void* a_out, void* gate_out, const float* bias,
-            const float* film, long long film_stride, long long ppb, cudaStream_t st);
-int gemm_tn(const void* X, const void* Y, int batch, long long ppb, int slices, float* partial, cudaStream_t st);
+            const float* film, long long film_stride, long long ppb, cudaStream_t st, const void* gate_mul = nullptr);
+int gemm_tn(const void* X, const void* Y, int batch, long long ppb, int slices, float* partial, cudaStream_t st,
+            float* colsum = nullptr);
 // mapping.cu
 int mapping_film(const float* const* w, const float* const* b, const float* z, int B, int z_dim, int n_layers, int layer0,
                  int n_film_total, const float* avg_f, const float* avg_p, float psi, float* h_scratch, float* film,

@@ -10,10 +10,11 @@
 // One persistent CTA per SM, 192 threads: warps 0..3 epilogue (one TMEM lane quadrant each), warp 4 loader
 // (16-byte cp.async into the 128B-swizzled UMMA layouts -- the operands are plain row-major tensors, no tensor maps),
 // warp 5 MMA issuer (elect.sync).  gemm_nt keeps the whole 256 x 256 fp16 B matrix resident in shared memory (128 KB)
-// next to one 128-row A tile (64 KB) and double-buffers the accumulator in TMEM (2 x 256 columns), so the load of tile
-// i+1 and its MMAs overlap the epilogue of tile i; it is HBM-bound (64 KB in, 64-128 KB out per 8.4 MFLOP... per tile:
-// 16.8 MFLOP against >= 128 KB, i.e. ~130 FLOP/B vs the machine's 260).  gemm_tn streams 64-point stages (2 x 32 KB)
-// through a 3-deep ring and holds the 256 x 256 fp32 result in all 512 TMEM columns.
+// and streams A through a 5-deep ring of 64-wide k-chunks ([128 rows][64 k], 16 KB each); the accumulator is
+// double-buffered in TMEM (2 x 256 columns), so the loads and MMAs of tile i+1 overlap the epilogue of tile i.  It is
+// HBM-bound: 16.8 MFLOP per tile against >= 128 KB moved, ~130 FLOP/B vs the machine's 260.  gemm_tn streams 64-point
+// stages (2 x 32 KB) through a 3-deep ring and holds the 256 x 256 fp32 result in all 512 TMEM columns.  The loader never
+// waits for its own copies: cp.async.mbarrier.arrive.noinc hands each lane's arrival to the stage's mbarrier.
 #include "common.cuh"
 #include "tc5.cuh"
 
@@ -30,6 +31,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// the mbarrier receives this thread's arrival once all of its earlier cp.async have landed (no wait in the loader: the
+// ring stays full); the consumer runs fence.proxy.async after its wait, before handing the buffer to the tensor core
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
 }
@@ -47,6 +53,7 @@ struct NtArgs {
     __half* C16;          // (M, 256) fp16 out, or (FiLM epilogue) both of:
     __half* a_out;        // (M, 256) sin(f (c + bias) + p)
     __half* gate_out;     // (M, 256) f cos(f (c + bias) + p)
+    const __half* gate_mul;  // optional (M, 256): the fp16 output is multiplied by it (dZ' = (dZ W) * gate of the layer below)
     const float* bias;    // (256)
     const float* film;    // image 0's [2][256] block of the layer
     long long film_stride, ppb;
@@ -54,8 +61,9 @@ struct NtArgs {
 };
 
 constexpr uint32_t NT_SB = 0;                 // B: 4 k-chunks of [256 rows][64 k] = 4 x 32 KB
-constexpr uint32_t NT_SA = 131072;            // A tile: 4 k-chunks of [128 rows][64 k] = 4 x 16 KB
-constexpr uint32_t NT_BAR = NT_SA + 65536;    // barriers + tmem slot
+constexpr uint32_t NT_SA = 131072;            // A ring: NT_RING k-chunks of [128 rows][64 k], 16 KB each
+constexpr int NT_RING = 5;                    // one tile (4 chunks) consumed while the next one streams in
+constexpr uint32_t NT_BAR = NT_SA + NT_RING * 16384;    // barriers + tmem slot
 constexpr uint32_t NT_FILM = NT_BAR + 128;    // [3][256] floats: f, p, bias of the tile's first image
 constexpr uint32_t NT_SMEM = NT_FILM + 3 * 256 * 4;
 
@@ -63,12 +71,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_b = sbase + NT_BAR, bar_afull = bar_b + 8, bar_aempty = bar_b + 16;
-    const uint32_t bar_accfull = bar_b + 24 /* [2] */, bar_accempty = bar_b + 40 /* [2] */;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + NT_BAR + 64);
+    const uint32_t bar_b = sbase + NT_BAR;
+    const uint32_t bar_accfull = bar_b + 8 /* [2] */, bar_accempty = bar_b + 24 /* [2] */;
+    const uint32_t bar_afull = bar_b + 40 /* [NT_RING] */, bar_aempty = bar_afull + 8 * NT_RING /* [NT_RING] */;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + NT_BAR + 120);
     float* s_film = reinterpret_cast<float*>(smem + NT_FILM);
     if (threadIdx.x == 0) {
-        mbar_init(bar_b, 1); mbar_init(bar_afull, 1); mbar_init(bar_aempty, 1);
+        mbar_init(bar_b, 32);
+        for (int i = 0; i < NT_RING; ++i) { mbar_init(bar_afull + 8 * i, 32); mbar_init(bar_aempty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_accfull + 8 * i, 1); mbar_init(bar_accempty + 8 * i, 4); }
         fence_barrier_init();
     }
@@ -88,44 +98,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
             const int row = i >> 5, kc = (i >> 3) & 3, j = i & 7;
             cp_async16(sbase + NT_SB + kc * 32768 + fn_sw128_offset(row, j * 8), a.B + row * 256 + kc * 64 + j * 8);
         }
-        cp_async_wait_all();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_b);
-        uint32_t it = 0;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            mbar_wait(bar_aempty, (it & 1) ^ 1);
+        cp_async_arrive_noinc(bar_b);
+        uint32_t ch = 0;                                   // running k-chunk number: ring slot ch % NT_RING
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const long long m0 = t * 128;
-            for (int i = lane; i < 128 * 32; i += 32) {
-                const int row = i >> 5, kc = (i >> 3) & 3, j = i & 7;
-                const uint32_t dst = sbase + NT_SA + kc * 16384 + fn_sw128_offset(row, j * 8);
-                if (m0 + row < a.M) cp_async16(dst, a.A + (m0 + row) * 256 + kc * 64 + j * 8);
-                else st_shared_zero16(dst);
+            for (int kc = 0; kc < 4; ++kc, ++ch) {
+                const uint32_t slot = ch % NT_RING, use = ch / NT_RING;
+                mbar_wait(bar_aempty + 8 * slot, (use & 1) ^ 1);
+                const uint32_t base = sbase + NT_SA + slot * 16384;
+                for (int i = lane; i < 128 * 8; i += 32) {           // (row, 16-byte piece) of this 64-wide k-chunk
+                    const int row = i >> 3, j = i & 7;
+                    const uint32_t dst = base + fn_sw128_offset(row, j * 8);
+                    if (m0 + row < a.M) cp_async16(dst, a.A + (m0 + row) * 256 + kc * 64 + j * 8);
+                    else st_shared_zero16(dst);
+                }
+                cp_async_arrive_noinc(bar_afull + 8 * slot);
             }
-            cp_async_wait_all();
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_afull);
         }
     } else if (warp == kMmaWarp) {
         mbar_wait(bar_b, 0);
+        fence_async_smem();
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc_f16(256, 0, 0);
         const uint32_t a_lo = (sbase + NT_SA) >> 4, b_lo = (sbase + NT_SB) >> 4;
-        uint32_t it = 0;
+        uint32_t it = 0, ch = 0;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t buf = it & 1, use = it >> 1;
             mbar_wait(bar_accempty + 8 * buf, (use & 1) ^ 1);
-            mbar_wait(bar_afull, it & 1);
             tc_fence_after();
             const uint32_t d = tmem_base + buf * 256u;
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc)
+            for (int kc = 0; kc < 4; ++kc, ++ch) {
+                const uint32_t slot = ch % NT_RING, cuse = ch / NT_RING;
+                mbar_wait(bar_afull + 8 * slot, cuse & 1);
+                fence_async_smem();          // the chunk was written by cp.async (generic proxy): order it before the MMA's reads
+                tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    tc_mma_f16_elect(d, kDescHi | (uint64_t)(a_lo + kc * (16384 >> 4) + 2 * k),
+                    tc_mma_f16_elect(d, kDescHi | (uint64_t)(a_lo + slot * (16384 >> 4) + 2 * k),
                                      kDescHi | (uint64_t)(b_lo + kc * (32768 >> 4) + 2 * k), idesc, (kc | k) ? 1u : 0u);
-            tc_commit_elect(bar_aempty);
+                tc_commit_elect(bar_aempty + 8 * slot);
+            }
             tc_commit_elect(bar_accfull + 8 * buf);
         }
     } else {
@@ -184,6 +196,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
                             make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                         __uint_as_float(r[4 * j + 3]));
                 } else {
+                    if (a.gate_mul) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 gq = *reinterpret_cast<const uint4*>(a.gate_mul + m * 256 + g * 32 + j * 8);
+                            const __half2* g2 = reinterpret_cast<const __half2*>(&gq);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 gf = __half22float2(g2[i]);
+                                r[8 * j + 2 * i] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i]) * gf.x);
+                                r[8 * j + 2 * i + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * i + 1]) * gf.y);
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 pk;
@@ -213,6 +238,7 @@ struct TnArgs {
     const __half* X;      // (B * ppb, 256): rows of image b are [b * ppb, (b + 1) * ppb)
     const __half* Y;      // (B * ppb, 256)
     float* partial;       // (B, slices, 256, 256): X_b^T Y_b summed over this CTA's stages
+    float* colsum;        // optional (B, slices, 256): column sums of X over the same stages (the bias / phase gradients)
     long long ppb;
     int slices;
 };
@@ -229,7 +255,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
     const uint32_t bar_full = sbase + TN_BAR /* [3] */, bar_empty = bar_full + 24 /* [3] */, bar_done = bar_full + 48;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TN_BAR + 64);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TN_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        // a stage is released by the MMA's commit and, when column sums are wanted, by the four epilogue warps reading it
+        for (int i = 0; i < TN_STAGES; ++i) { mbar_init(bar_full + 8 * i, 32); mbar_init(bar_empty + 8 * i, a.colsum ? 5 : 1); }
         mbar_init(bar_done, 1);
         fence_barrier_init();
     }
@@ -265,10 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
                     st_shared_zero16(sy + off);
                 }
             }
-            cp_async_wait_all();
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full + 8 * st);
+            cp_async_arrive_noinc(bar_full + 8 * st);
         }
     } else if (warp == kMmaWarp) {
         constexpr uint32_t idesc = umma_idesc_f16(256, 1, 1);
@@ -276,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
         for (long long i = 0; i < n_mine; ++i) {
             const uint32_t st = (uint32_t)(i % TN_STAGES), use = (uint32_t)(i / TN_STAGES);
             mbar_wait(bar_full + 8 * st, use & 1);
+            fence_async_smem();
             tc_fence_after();
             const uint32_t x_lo = (sbase + st * TN_STAGE_BYTES) >> 4, y_lo = x_lo + (32768 >> 4);
 #pragma unroll
@@ -289,6 +314,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
         tc_commit_elect(bar_done);
     } else {
         const int q = warp & 3, row = q * 32 + lane;
+        if (a.colsum) {
+            // while the tensor core works: column sums of X straight from the staged tiles.  Thread t owns features 2t,
+            // 2t+1; element (k, f) of a stage sits at (k/8)*4096 + (f/64)*1024 + (k%8)*128 + (((f%64)/8) ^ (k%8))*16 + (f%8)*2
+            const int t = threadIdx.x, f = 2 * t;
+            float s0 = 0.f, s1 = 0.f;
+            for (long long i = 0; i < n_mine; ++i) {
+                const uint32_t st = (uint32_t)(i % TN_STAGES), use = (uint32_t)(i / TN_STAGES);
+                mbar_wait(bar_full + 8 * st, use & 1);
+                const unsigned char* sx = smem + st * TN_STAGE_BYTES + (f >> 6) * 1024 + (f & 7) * 2;
+#pragma unroll 8
+                for (int k = 0; k < 64; ++k) {
+                    const __half2 v = *reinterpret_cast<const __half2*>(sx + (k >> 3) * 4096 + (k & 7) * 128 + ((((f & 63) >> 3) ^ (k & 7)) << 4));
+                    const float2 vf = __half22float2(v);
+                    s0 += vf.x; s1 += vf.y;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * st);
+            }
+            float* cs = a.colsum + ((size_t)b * a.slices + slice) * 256;
+            cs[f] = s0; cs[f + 1] = s1;
+        }
         mbar_wait(bar_done, 0);
         tc_fence_after();
         float* out = a.partial + ((size_t)b * a.slices + slice) * 65536;
@@ -322,11 +368,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
 }  // namespace
 
 int gemm_nt(const void* A, const void* B, long long M, float* c32, void* c16, void* a_out, void* gate_out, const float* bias,
-            const float* film, long long film_stride, long long ppb, cudaStream_t st) {
+            const float* film, long long film_stride, long long ppb, cudaStream_t st, const void* gate_mul) {
     static_assert(NT_SMEM <= 232448, "gemm_nt shared memory");
     NtArgs a;
     a.A = (const __half*)A; a.B = (const __half*)B; a.C32 = c32; a.C16 = (__half*)c16; a.a_out = (__half*)a_out;
-    a.gate_out = (__half*)gate_out; a.bias = bias; a.film = film; a.film_stride = film_stride; a.ppb = ppb > 0 ? ppb : 1; a.M = M;
+    a.gate_out = (__half*)gate_out; a.gate_mul = (const __half*)gate_mul; a.bias = bias; a.film = film; a.film_stride = film_stride; a.ppb = ppb > 0 ? ppb : 1; a.M = M;
     if (M <= 0) return 0;
     static std::atomic<int> set[kMaxDevices];
     FN_CUDA_OK(ensure_dynamic_smem(gemm_nt_kernel, set, (int)NT_SMEM));
@@ -337,10 +383,10 @@ int gemm_nt(const void* A, const void* B, long long M, float* c32, void* c16, vo
     return 0;
 }
 
-int gemm_tn(const void* X, const void* Y, int batch, long long ppb, int slices, float* partial, cudaStream_t st) {
+int gemm_tn(const void* X, const void* Y, int batch, long long ppb, int slices, float* partial, cudaStream_t st, float* colsum) {
     static_assert(TN_SMEM <= 232448, "gemm_tn shared memory");
     TnArgs a;
-    a.X = (const __half*)X; a.Y = (const __half*)Y; a.partial = partial; a.ppb = ppb; a.slices = slices;
+    a.X = (const __half*)X; a.Y = (const __half*)Y; a.partial = partial; a.colsum = colsum; a.ppb = ppb; a.slices = slices;
     static std::atomic<int> set[kMaxDevices];
     FN_CUDA_OK(ensure_dynamic_smem(gemm_tn_kernel, set, (int)TN_SMEM));
     gemm_tn_kernel<<<dim3(slices, batch), kThreads, TN_SMEM, st>>>(a);

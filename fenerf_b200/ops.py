@@ -378,15 +378,17 @@ def mapping_film(net, z, film, first_layer, n_layers, avg=None, psi=1.0):
 # --------------------------------------------------------------------------------------------
 # tcgen05 GEMMs of the backward (csrc/gemm5.cu)
 # --------------------------------------------------------------------------------------------
-def gemm_nt(a16, b16, out_dtype=torch.float32):
-    """(M, 256) fp16 . (256, 256)^T fp16 -> (M, 256) fp32 or fp16 (fenerf_gemm_nt_f16)."""
+def gemm_nt(a16, b16, out_dtype=torch.float32, gate=None):
+    """(M, 256) fp16 . (256, 256)^T fp16 -> (M, 256) fp32 or fp16 (fenerf_gemm_nt_f16); `gate` (M, 256) fp16 multiplies
+    the fp16 output in the epilogue."""
     dev = a16.device
     m = a16.shape[0]
     out = torch.empty((m, 256), dtype=out_dtype, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().fenerf_gemm_nt_f16(
             _chk(a16, "A", dev, torch.float16), _chk(b16, "B", dev, torch.float16), m,
-            out.data_ptr() if out_dtype == torch.float32 else 0, out.data_ptr() if out_dtype == torch.float16 else 0, _stream(dev)))
+            out.data_ptr() if out_dtype == torch.float32 else 0, out.data_ptr() if out_dtype == torch.float16 else 0,
+            _chk(gate, "gate", dev, torch.float16), _stream(dev)))
     return out
 
 
@@ -403,15 +405,17 @@ def gemm_nt_film(a16, w16, bias, film, b0, layer, ppb):
     return a_out, g_out
 
 
-def gemm_tn(x16, y16, batch, ppb, slices=None):
+def gemm_tn(x16, y16, batch, ppb, slices=None, colsum=False):
     """Per image b: X_b^T Y_b with X, Y (batch * ppb, 256) fp16 -> (batch, 256, 256) fp32 (fenerf_gemm_tn_f16; the
-    split-K partials of the CTAs are summed here)."""
+    split-K partials of the CTAs are summed here).  colsum=True also returns the column sums of X per image (batch, 256)."""
     dev = x16.device
     if slices is None:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         slices = max(1, min((ppb + 63) // 64, (sms + batch - 1) // batch))
     partial = torch.empty((batch, slices, 256, 256), dtype=torch.float32, device=dev)
+    cs = torch.empty((batch, slices, 256), dtype=torch.float32, device=dev) if colsum else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().fenerf_gemm_tn_f16(_chk(x16, "X", dev, torch.float16), _chk(y16, "Y", dev, torch.float16), batch,
-                                                 ppb, slices, partial.data_ptr(), _stream(dev)))
-    return partial.sum(1) if slices > 1 else partial[:, 0]
+                                                 ppb, slices, partial.data_ptr(), cs.data_ptr() if colsum else 0, _stream(dev)))
+    out = partial.sum(1) if slices > 1 else partial[:, 0]
+    return (out, cs.sum(1)) if colsum else out

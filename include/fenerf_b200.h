@@ -315,17 +315,20 @@ int fenerf_frames_to_u8(const float* frames, int32_t batch, int32_t channels, in
 
 /* The 256-wide products of a FiLM layer's backward on tcgen05 (csrc/gemm5.cu); fp16 row-major operands, fp32 accumulate.
  *   fenerf_gemm_nt_f16   C (M, 256) = A (M, 256) . B (256, 256)^T  -> c_f32 or c_f16 (exactly one non-NULL)
- *                        (dA' = dZ W: pass B = W^T)
+ *                        (dA' = dZ W: pass B = W^T); optional gate_mul (M, 256) fp16 multiplies the fp16 output in the
+ *                        epilogue: dZ of the layer below = (dZ W) * its gate, without a pass of its own
  *   fenerf_gemm_nt_film  the recompute of a layer with its epilogue fused: z = A W^T never leaves the SM,
  *                        a_out = sin(f (z + bias) + p), gate_out = f cos(f (z + bias) + p), both (M, 256) fp16;
  *                        film_layer / film_batch_stride / points_per_batch as in fenerf_film_forward_stash
  *   fenerf_gemm_tn_f16   partial (batch, slices, 256, 256) fp32: for image b, slice s the sum over its 64-point stages
- *                        s, s + slices, ... of X[p, :]^T Y[p, :]  (dW_b = dZ^T a = the sum over the slices)      */
-int fenerf_gemm_nt_f16(const void* A, const void* B, int64_t M, float* c_f32, void* c_f16, void* stream);
+ *                        s, s + slices, ... of X[p, :]^T Y[p, :]  (dW_b = dZ^T a = the sum over the slices); optional
+ *                        colsum (batch, slices, 256): column sums of X over the same stages (= d bias), computed by the
+ *                        epilogue warps from the staged tiles while the tensor core runs                              */
+int fenerf_gemm_nt_f16(const void* A, const void* B, int64_t M, float* c_f32, void* c_f16, const void* gate_mul, void* stream);
 int fenerf_gemm_nt_film(const void* A, const void* W, int64_t M, const float* bias, const float* film_layer,
                         int64_t film_batch_stride, int64_t points_per_batch, void* a_out, void* gate_out, void* stream);
 int fenerf_gemm_tn_f16(const void* X, const void* Y, int32_t batch, int64_t points_per_batch, int32_t slices, float* partial,
-                       void* stream);
+                       float* colsum, void* stream);
 
 /* d pixels (B, C-1, H, W) -> d raw outputs.  Backward of the merge + fancy_integration + softmax / *2-1
  * epilogue (generators.py:85-104, volumetric_rendering.py:18-50); same arguments as fenerf_composite.
