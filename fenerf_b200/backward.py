@@ -25,7 +25,9 @@ taken from max|d raw| on the device (no host sync) and unscaled at the end.
 The three 256-wide products per layer run on tcgen05 (csrc/gemm5.cu: ``fenerf_gemm_nt_film`` -- the recompute with its FiLM
 epilogue fused, ``fenerf_gemm_nt_f16`` for dA' = dZ W, ``fenerf_gemm_tn_f16`` split-K for the per-image dW); only the narrow
 products (heads, the 3 / 35-wide inputs) go to the library.  ``FENERF_B200_BWD_GEMM=cublas`` switches the wide ones back
-(A/B timing); ``precision='exact'`` always uses fp32 library GEMMs.
+(A/B timing); ``precision='exact'`` always uses fp32 library GEMMs.  (The kernels can also fold the next layer's gate multiply
+into the dA product's epilogue and produce the bias column sums from the dW kernel's staged tiles -- measured: the gate kernel's
+17 ms disappear but the two GEMMs slow down by as much, both being HBM-bound; the chain below keeps the separate gate kernel.)
 """
 import ctypes as C
 
@@ -205,12 +207,11 @@ class _FieldBackward:
             _ptr(xin), kx, _ptr(wx), a.data_ptr(), g.data_ptr(), self.dtc, _stream(self.dev)))
         return a, g
 
-    def _gate(self, dA, gate, idx, b0, b1, P, ppb, add_colsum=True):
+    def _gate(self, dA, gate, idx, b0, b1, P, ppb):
         cs = self.colsum[b0:b1, idx]
         tmp = torch.zeros((b1 - b0, 256), dtype=torch.float32, device=self.dev)
         _lib.check(_lib.lib().fenerf_gate_backward(dA.data_ptr(), gate.data_ptr(), P, ppb, tmp.data_ptr(), self.dtc, _stream(self.dev)))
-        if add_colsum:      # (on the tcgen05 path the column sums come out of fenerf_gemm_tn_f16 instead)
-            cs += tmp
+        cs += tmp
 
     def _chunk(self, points, dirs, dir_group, lock_dirs, raw, d_raw, b0, b1):
         lib = _lib.lib()
@@ -256,51 +257,35 @@ class _FieldBackward:
             self.d_heads_w += _mm32(dH.t(), A[T - 1])
             self.d_heads_b += dH.float().sum(0)
             # ---- colour branch, top down ----
-            dA = torch.mm(dRGB, self.Wrgb16)                                   # (P, 256)
-            self._gate(dA, Gt[T + Cn - 1], T + Cn - 1, b0, b1, P, ppb, add_colsum=not own)     # dA is dZ of the top colour layer
+            dA = torch.mm(dRGB, self.Wrgb16)                                   # (P, 256) fp16
             for j in range(Cn - 1, -1, -1):
                 idx = T + j
+                self._gate(dA, Gt[idx], idx, b0, b1, P, ppb)                   # dA is dZ now
                 a_in = A[idx - 1]
                 dz3 = dA.view(k, ppb, 256).transpose(1, 2)
-                if own:     # per-image dW on tcgen05, the column sums (d bias) ride along
-                    dwb, cs = ops.gemm_tn(dA, a_in, k, ppb, colsum=True)
-                    self.dW_b[idx][b0:b1] += dwb
-                    self.colsum[b0:b1, idx] += cs
-                else:
-                    self.dW_b[idx][b0:b1] += _bmm32(dz3, a_in.view(k, ppb, 256))
+                self.dW_b[idx][b0:b1] += ops.gemm_tn(dA, a_in, k, ppb) if own else _bmm32(dz3, a_in.view(k, ppb, 256))
                 if j == 0:
                     e16 = torch.zeros((P, self.kx_pad), dtype=self.dt, device=dev)
                     e16[:, :self.kx] = extras
                     self.dWx_b[b0:b1] += _bmm32(dz3, e16.view(k, ppb, self.kx_pad))
                     if spec.grid_channels:
-                        d_feat = torch.mm(dA, self.Wfeat16).contiguous()       # (P, G)
+                        d_feat = torch.mm(dA, self.Wfeat16).contiguous()       # (P, G) fp16
                         _lib.check(lib.fenerf_grid_scatter_add(C.byref(self.packed.desc), points.data_ptr(), d_feat.data_ptr(),
                                                                d_feat.shape[1], P, self.grid_grad_cl.data_ptr(), self.dtc, st))
-                    dA = ops.gemm_nt(dA, self.WcT16[0], torch.float16) if own else torch.mm(dA, self.Wc16[0])
-                elif own:   # dZ of the layer below in one kernel: (dZ W) * its gate
-                    dA = ops.gemm_nt(dA, self.WcT16[j], torch.float16, gate=Gt[idx - 1])
-                else:
-                    dA = torch.mm(dA, self.Wc16[j])
-                    self._gate(dA, Gt[idx - 1], idx - 1, b0, b1, P, ppb)
+                dA = ops.gemm_nt(dA, self.WcT16[j], torch.float16) if own else torch.mm(dA, self.Wc16[j])
                 A[idx], Gt[idx] = None, None
             # ---- trunk: colour-branch gradient + sigma / label heads ----
             dA += torch.mm(dH.float(), self.Wheads32)
-            self._gate(dA, Gt[T - 1], T - 1, b0, b1, P, ppb, add_colsum=not own)
             for l in range(T - 1, 0, -1):
+                self._gate(dA, Gt[l], l, b0, b1, P, ppb)
                 if own:
-                    dwb, cs = ops.gemm_tn(dA, A[l - 1], k, ppb, colsum=True)
-                    self.dW_b[l][b0:b1] += dwb
-                    self.colsum[b0:b1, l] += cs
-                    if l > 1:
-                        dA = ops.gemm_nt(dA, self.WhT16[l], torch.float16, gate=Gt[l - 1])
-                    else:   # the first layer has no 256-wide dW (and so no fused column sums): plain product, then the gate kernel
-                        dA = ops.gemm_nt(dA, self.WhT16[l], torch.float16)
-                        self._gate(dA, Gt[0], 0, b0, b1, P, ppb)
+                    self.dW_b[l][b0:b1] += ops.gemm_tn(dA, A[l - 1], k, ppb)
+                    dA = ops.gemm_nt(dA, self.WhT16[l], torch.float16)
                 else:
                     self.dW_b[l][b0:b1] += _bmm32(dA.view(k, ppb, 256).transpose(1, 2), A[l - 1].view(k, ppb, 256))
                     dA = torch.mm(dA, self.Wh16[l])
-                    self._gate(dA, Gt[l - 1], l - 1, b0, b1, P, ppb)
                 A[l], Gt[l] = None, None
+            self._gate(dA, Gt[0], 0, b0, b1, P, ppb)
             x16 = torch.zeros((P, 8), dtype=self.dt, device=dev)
             x16[:, :3] = x
             self.dW_b[0][b0:b1] += _bmm32(dA.view(k, ppb, 256).transpose(1, 2), x16.view(k, ppb, 8))

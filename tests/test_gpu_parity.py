@@ -576,6 +576,9 @@ def test_tcgen05_gemm_nt_against_fp32_matmul(m):
     scale = want.abs().max()
     assert (got32 - want).abs().max() <= 2e-5 * scale, float((got32 - want).abs().max() / scale)
     assert (got16.float() - want).abs().max() <= 1e-3 * scale
+    gate = (torch.randn(m, 256, device=DEV, generator=g) * 5).half()      # optional epilogue: output * gate
+    gated = ops.gemm_nt(a, w, torch.float16, gate=gate)
+    assert (gated.float() - want * gate.float()).abs().max() <= 2e-3 * (want * gate.float()).abs().max()
     # the fused FiLM epilogue
     B, ppb = 2, (m + 1) // 2
     mm = B * ppb
@@ -598,6 +601,10 @@ def test_tcgen05_gemm_tn_against_fp32_bmm(batch, ppb, slices):
     got = ops.gemm_tn(x, y, batch, ppb, slices)
     scale = want.abs().max()
     assert (got - want).abs().max() <= 5e-5 * scale, float((got - want).abs().max() / scale)
+    got2, cs = ops.gemm_tn(x, y, batch, ppb, slices, colsum=True)         # optional: column sums of X ride along
+    assert torch.equal(got2, got)
+    want_cs = x.float().reshape(batch, ppb, 256).sum(1)
+    assert (cs - want_cs).abs().max() <= 1e-4 * max(1.0, float(want_cs.abs().max()))
 
 
 def test_frame_consumers_match_the_reference_loops():
