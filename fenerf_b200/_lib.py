@@ -114,7 +114,7 @@ def _declare(lib):
     lib.fenerf_gemm_nt_f16.restype = C.c_int
     lib.fenerf_gemm_nt_f16.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.fenerf_gemm_nt_film.restype = C.c_int
-    lib.fenerf_gemm_nt_film.argtypes = [vp, vp, i64, vp, vp, i64, i64, vp, vp, vp]
+    lib.fenerf_gemm_nt_film.argtypes = [vp, vp, i64, vp, vp, i64, i64, vp, vp, vp, vp, vp]
     lib.fenerf_gemm_tn_f16.restype = C.c_int
     lib.fenerf_gemm_tn_f16.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
     lib.fenerf_debug_stage_times.restype = C.c_int

@@ -168,6 +168,9 @@ class _FieldBackward:
         # dA' = dZ W on the tcgen05 NT kernel wants the transposed weights as its (N, K) operand
         self.WhT16 = [None] + [w.t().contiguous() for w in self.Wh16[1:]] if self.own_gemm else None
         self.WcT16 = [w.t().contiguous() for w in self.Wc16] if self.own_gemm else None
+        if self.own_gemm:
+            self.Wn64 = torch.zeros((256, 64), dtype=torch.float16, device=dev)
+            self.Wn64[:, :self.kx] = self.Wc0x_narrow
         L = self.spec.label_dim
         self.L = L
         heads = torch.zeros((32, 256), dtype=torch.float32, device=dev)
@@ -238,9 +241,14 @@ class _FieldBackward:
                     A[l], Gt[l] = ops.gemm_nt_film(A[l - 1], self.Wh16[l], self.bias[l], self.film, b0, l, ppb)
                 else:
                     A[l], Gt[l] = self._stash(_mm32(A[l - 1], self.Wh16[l].t()), l, b0, P, ppb)
-            z = ops.gemm_nt(A[T - 1], self.Wc16[0]) if own else _mm32(A[T - 1], self.Wc16[0].t())
-            A[T], Gt[T] = self._stash(z, T, b0, P, ppb, xin=extras, wx=self.Wc0x_narrow)
-            del z
+            if own:     # the narrow inputs [dir, grid features] ride as a fifth 64-wide k-chunk of the same kernel
+                e64 = torch.zeros((P, 64), dtype=torch.float16, device=dev)
+                e64[:, :self.kx] = extras
+                A[T], Gt[T] = ops.gemm_nt_film(A[T - 1], self.Wc16[0], self.bias[T], self.film, b0, T, ppb, narrow_in=e64,
+                                               narrow_w=self.Wn64)
+                del e64
+            else:
+                A[T], Gt[T] = self._stash(_mm32(A[T - 1], self.Wc16[0].t()), T, b0, P, ppb, xin=extras, wx=self.Wc0x_narrow)
             for j in range(1, Cn):
                 if own:
                     A[T + j], Gt[T + j] = ops.gemm_nt_film(A[T + j - 1], self.Wc16[j], self.bias[T + j], self.film, b0, T + j, ppb)

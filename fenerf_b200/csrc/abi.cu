@@ -321,11 +321,14 @@ int fenerf_gemm_nt_f16(const void* A, const void* B, int64_t M, float* c_f32, vo
 }
 
 int fenerf_gemm_nt_film(const void* A, const void* W, int64_t M, const float* bias, const float* film_layer,
-                        int64_t film_batch_stride, int64_t points_per_batch, void* a_out, void* gate_out, void* stream) {
+                        int64_t film_batch_stride, int64_t points_per_batch, const void* narrow_in, const void* narrow_w,
+                        void* a_out, void* gate_out, void* stream) {
     FN_REQUIRE(A && W && bias && film_layer && a_out && gate_out && M >= 0 && points_per_batch >= 1, "bad argument");
-    FN_REQUIRE((((uintptr_t)A | (uintptr_t)W | (uintptr_t)a_out | (uintptr_t)gate_out) & 15) == 0, "operands must be 16-byte aligned");
+    FN_REQUIRE((narrow_in == nullptr) == (narrow_w == nullptr), "narrow_in and narrow_w go together");
+    FN_REQUIRE((((uintptr_t)A | (uintptr_t)W | (uintptr_t)a_out | (uintptr_t)gate_out | (uintptr_t)narrow_in | (uintptr_t)narrow_w) & 15) == 0,
+               "operands must be 16-byte aligned");
     return gemm_nt(A, W, M, nullptr, nullptr, a_out, gate_out, bias, film_layer, film_batch_stride, points_per_batch,
-                   (cudaStream_t)stream);
+                   (cudaStream_t)stream, nullptr, narrow_in, narrow_w);
 }
 
 int fenerf_gemm_tn_f16(const void* X, const void* Y, int32_t batch, int64_t points_per_batch, int32_t slices, float* partial,

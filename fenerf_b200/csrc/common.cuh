@@ -111,7 +111,8 @@ int composite(const fenerf_render_desc* rd, int C, const float* raw_c, const flo
 
 // gemm5.cu
 int gemm_nt(const void* A, const void* B, long long M, float* c32, void* c16, void* a_out, void* gate_out, const float* bias,
-            const float* film, long long film_stride, long long ppb, cudaStream_t st, const void* gate_mul = nullptr);
+            const float* film, long long film_stride, long long ppb, cudaStream_t st, const void* gate_mul = nullptr,
+            const void* A2 = nullptr, const void* B2 = nullptr);
 int gemm_tn(const void* X, const void* Y, int batch, long long ppb, int slices, float* partial, cudaStream_t st,
             float* colsum = nullptr);
 // mapping.cu

@@ -10,7 +10,8 @@
 // One persistent CTA per SM, 192 threads: warps 0..3 epilogue (one TMEM lane quadrant each), warp 4 loader
 // (16-byte cp.async into the 128B-swizzled UMMA layouts -- the operands are plain row-major tensors, no tensor maps),
 // warp 5 MMA issuer (elect.sync).  gemm_nt keeps the whole 256 x 256 fp16 B matrix resident in shared memory (128 KB)
-// and streams A through a 5-deep ring of 64-wide k-chunks ([128 rows][64 k], 16 KB each); the accumulator is
+// (+ 32 KB for an optional fifth, narrow k-chunk) and streams A through a 3-deep ring of 64-wide k-chunks ([128 rows][64 k],
+// 16 KB each); the accumulator is
 // double-buffered in TMEM (2 x 256 columns), so the loads and MMAs of tile i+1 overlap the epilogue of tile i.  It is
 // HBM-bound: 16.8 MFLOP per tile against >= 128 KB moved, ~130 FLOP/B vs the machine's 260.  gemm_tn streams 64-point
 // stages (2 x 32 KB) through a 3-deep ring and holds the 256 x 256 fp32 result in all 512 TMEM columns.  The loader never
@@ -54,15 +55,17 @@ struct NtArgs {
     __half* a_out;        // (M, 256) sin(f (c + bias) + p)
     __half* gate_out;     // (M, 256) f cos(f (c + bias) + p)
     const __half* gate_mul;  // optional (M, 256): the fp16 output is multiplied by it (dZ' = (dZ W) * gate of the layer below)
+    const __half* A2;     // optional fifth k-chunk: narrow inputs (M, 64) fp16 (zero padded) ...
+    const __half* B2;     // ... against (256, 64) fp16: C += A2 B2^T  (the first colour layer's [dir, grid features])
     const float* bias;    // (256)
     const float* film;    // image 0's [2][256] block of the layer
     long long film_stride, ppb;
     long long M;
 };
 
-constexpr uint32_t NT_SB = 0;                 // B: 4 k-chunks of [256 rows][64 k] = 4 x 32 KB
-constexpr uint32_t NT_SA = 131072;            // A ring: NT_RING k-chunks of [128 rows][64 k], 16 KB each
-constexpr int NT_RING = 5;                    // one tile (4 chunks) consumed while the next one streams in
+constexpr uint32_t NT_SB = 0;                 // B: 5 k-chunks of [256 rows][64 k] = 5 x 32 KB (the fifth only with narrow inputs)
+constexpr uint32_t NT_SA = 163840;            // A ring: NT_RING k-chunks of [128 rows][64 k], 16 KB each
+constexpr int NT_RING = 3;
 constexpr uint32_t NT_BAR = NT_SA + NT_RING * 16384;    // barriers + tmem slot
 constexpr uint32_t NT_FILM = NT_BAR + 128;    // [3][256] floats: f, p, bias of the tile's first image
 constexpr uint32_t NT_SMEM = NT_FILM + 3 * 256 * 4;
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const long long n_tiles = (a.M + 127) / 128;
+    const int n_chunks = a.A2 ? 5 : 4;
 
     if (warp == kLoadWarp) {
         // ---- B once: (row, kc, piece) -> kc * 32 KB + sw128(row, piece * 8)
@@ -98,18 +102,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
             const int row = i >> 5, kc = (i >> 3) & 3, j = i & 7;
             cp_async16(sbase + NT_SB + kc * 32768 + fn_sw128_offset(row, j * 8), a.B + row * 256 + kc * 64 + j * 8);
         }
+        if (a.A2)
+            for (int i = lane; i < 256 * 8; i += 32) {
+                const int row = i >> 3, j = i & 7;
+                cp_async16(sbase + NT_SB + 4 * 32768 + fn_sw128_offset(row, j * 8), a.B2 + row * 64 + j * 8);
+            }
         cp_async_arrive_noinc(bar_b);
         uint32_t ch = 0;                                   // running k-chunk number: ring slot ch % NT_RING
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const long long m0 = t * 128;
-            for (int kc = 0; kc < 4; ++kc, ++ch) {
+            for (int kc = 0; kc < n_chunks; ++kc, ++ch) {
                 const uint32_t slot = ch % NT_RING, use = ch / NT_RING;
                 mbar_wait(bar_aempty + 8 * slot, (use & 1) ^ 1);
                 const uint32_t base = sbase + NT_SA + slot * 16384;
+                const __half* src = kc < 4 ? a.A + kc * 64 : a.A2;
+                const long long ld = kc < 4 ? 256 : 64;
                 for (int i = lane; i < 128 * 8; i += 32) {           // (row, 16-byte piece) of this 64-wide k-chunk
                     const int row = i >> 3, j = i & 7;
                     const uint32_t dst = base + fn_sw128_offset(row, j * 8);
-                    if (m0 + row < a.M) cp_async16(dst, a.A + (m0 + row) * 256 + kc * 64 + j * 8);
+                    if (m0 + row < a.M) cp_async16(dst, src + (m0 + row) * ld + j * 8);
                     else st_shared_zero16(dst);
                 }
                 cp_async_arrive_noinc(bar_afull + 8 * slot);
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
             mbar_wait(bar_accempty + 8 * buf, (use & 1) ^ 1);
             tc_fence_after();
             const uint32_t d = tmem_base + buf * 256u;
-            for (int kc = 0; kc < 4; ++kc, ++ch) {
+            for (int kc = 0; kc < n_chunks; ++kc, ++ch) {
                 const uint32_t slot = ch % NT_RING, cuse = ch / NT_RING;
                 mbar_wait(bar_afull + 8 * slot, cuse & 1);
                 fence_async_smem();          // the chunk was written by cp.async (generic proxy): order it before the MMA's reads
@@ -368,11 +379,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
 }  // namespace
 
 int gemm_nt(const void* A, const void* B, long long M, float* c32, void* c16, void* a_out, void* gate_out, const float* bias,
-            const float* film, long long film_stride, long long ppb, cudaStream_t st, const void* gate_mul) {
+            const float* film, long long film_stride, long long ppb, cudaStream_t st, const void* gate_mul, const void* A2,
+            const void* B2) {
     static_assert(NT_SMEM <= 232448, "gemm_nt shared memory");
     NtArgs a;
     a.A = (const __half*)A; a.B = (const __half*)B; a.C32 = c32; a.C16 = (__half*)c16; a.a_out = (__half*)a_out;
-    a.gate_out = (__half*)gate_out; a.gate_mul = (const __half*)gate_mul; a.bias = bias; a.film = film; a.film_stride = film_stride; a.ppb = ppb > 0 ? ppb : 1; a.M = M;
+    a.gate_out = (__half*)gate_out; a.gate_mul = (const __half*)gate_mul; a.A2 = (const __half*)A2; a.B2 = (const __half*)B2;
+    a.bias = bias; a.film = film; a.film_stride = film_stride; a.ppb = ppb > 0 ? ppb : 1; a.M = M;
     if (M <= 0) return 0;
     static std::atomic<int> set[kMaxDevices];
     FN_CUDA_OK(ensure_dynamic_smem(gemm_nt_kernel, set, (int)NT_SMEM));

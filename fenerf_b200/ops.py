@@ -392,8 +392,9 @@ def gemm_nt(a16, b16, out_dtype=torch.float32, gate=None):
     return out
 
 
-def gemm_nt_film(a16, w16, bias, film, b0, layer, ppb):
-    """One FiLM layer's recompute with the epilogue fused (fenerf_gemm_nt_film): -> (a, gate), both (M, 256) fp16."""
+def gemm_nt_film(a16, w16, bias, film, b0, layer, ppb, narrow_in=None, narrow_w=None):
+    """One FiLM layer's recompute with the epilogue fused (fenerf_gemm_nt_film): -> (a, gate), both (M, 256) fp16.
+    narrow_in (M, 64) / narrow_w (256, 64) fp16 (zero padded): extra inputs of the layer."""
     dev = a16.device
     m = a16.shape[0]
     a_out = torch.empty((m, 256), dtype=torch.float16, device=dev)
@@ -401,7 +402,8 @@ def gemm_nt_film(a16, w16, bias, film, b0, layer, ppb):
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().fenerf_gemm_nt_film(
             _chk(a16, "A", dev, torch.float16), _chk(w16, "W", dev, torch.float16), m, _chk(bias, "bias", dev),
-            film[b0, layer].data_ptr(), film.stride(0), ppb, a_out.data_ptr(), g_out.data_ptr(), _stream(dev)))
+            film[b0, layer].data_ptr(), film.stride(0), ppb, _chk(narrow_in, "narrow_in", dev, torch.float16),
+            _chk(narrow_w, "narrow_w", dev, torch.float16), a_out.data_ptr(), g_out.data_ptr(), _stream(dev)))
     return a_out, g_out
 
 

@@ -319,14 +319,17 @@ int fenerf_frames_to_u8(const float* frames, int32_t batch, int32_t channels, in
  *                        epilogue: dZ of the layer below = (dZ W) * its gate, without a pass of its own
  *   fenerf_gemm_nt_film  the recompute of a layer with its epilogue fused: z = A W^T never leaves the SM,
  *                        a_out = sin(f (z + bias) + p), gate_out = f cos(f (z + bias) + p), both (M, 256) fp16;
- *                        film_layer / film_batch_stride / points_per_batch as in fenerf_film_forward_stash
+ *                        film_layer / film_batch_stride / points_per_batch as in fenerf_film_forward_stash; optional
+ *                        narrow_in (M, 64) fp16 / narrow_w (256, 64) fp16, zero padded: a fifth k-chunk, z += narrow_in
+ *                        narrow_w^T (the first colour layer's [dir, grid features] inputs, siren.py:1519-1522)
  *   fenerf_gemm_tn_f16   partial (batch, slices, 256, 256) fp32: for image b, slice s the sum over its 64-point stages
  *                        s, s + slices, ... of X[p, :]^T Y[p, :]  (dW_b = dZ^T a = the sum over the slices); optional
  *                        colsum (batch, slices, 256): column sums of X over the same stages (= d bias), computed by the
  *                        epilogue warps from the staged tiles while the tensor core runs                              */
 int fenerf_gemm_nt_f16(const void* A, const void* B, int64_t M, float* c_f32, void* c_f16, const void* gate_mul, void* stream);
 int fenerf_gemm_nt_film(const void* A, const void* W, int64_t M, const float* bias, const float* film_layer,
-                        int64_t film_batch_stride, int64_t points_per_batch, void* a_out, void* gate_out, void* stream);
+                        int64_t film_batch_stride, int64_t points_per_batch, const void* narrow_in, const void* narrow_w,
+                        void* a_out, void* gate_out, void* stream);
 int fenerf_gemm_tn_f16(const void* X, const void* Y, int32_t batch, int64_t points_per_batch, int32_t slices, float* partial,
                        float* colsum, void* stream);
 

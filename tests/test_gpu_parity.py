@@ -590,6 +590,13 @@ def test_tcgen05_gemm_nt_against_fp32_matmul(m):
     u = film[:, 1, 0].unsqueeze(1) * z + film[:, 1, 1].unsqueeze(1)
     assert (act.float().reshape(B, ppb, 256) - torch.sin(u)).abs().max() <= 2e-3
     assert (gate.float().reshape(B, ppb, 256) - film[:, 1, 0].unsqueeze(1) * torch.cos(u)).abs().max() <= 2e-3 * 50
+    # ... with a narrow fifth k-chunk (35 of 64 columns used)
+    xn = torch.zeros(mm, 64, device=DEV).half(); xn[:, :35] = (torch.randn(mm, 35, device=DEV, generator=g) * 0.3).half()
+    wn = torch.zeros(256, 64, device=DEV).half(); wn[:, :35] = (torch.randn(256, 35, device=DEV, generator=g) * 0.1).half()
+    act2, gate2 = ops.gemm_nt_film(a2, w, bias, film, 0, 1, ppb, narrow_in=xn, narrow_w=wn)
+    u2 = film[:, 1, 0].unsqueeze(1) * (z + (xn.float() @ wn.float().t()).reshape(B, ppb, 256)) + film[:, 1, 1].unsqueeze(1)
+    assert (act2.float().reshape(B, ppb, 256) - torch.sin(u2)).abs().max() <= 2e-3
+    assert (gate2.float().reshape(B, ppb, 256) - film[:, 1, 0].unsqueeze(1) * torch.cos(u2)).abs().max() <= 2e-3 * 50
 
 
 @pytest.mark.parametrize("batch,ppb,slices", [(1, 64, 1), (2, 200, 3), (3, 4096 * 3 + 5, None)])
