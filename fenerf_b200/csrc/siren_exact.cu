@@ -53,7 +53,7 @@ struct Smem {
     static constexpr int TM = 16 * P;
     // weight-slab pipeline depth: 2 for the dense tiles (two CTAs per SM must fit), 6 for the small
     // gather tiles whose 256 FFMA per slab cannot hide an L2 round trip behind a single prefetch
-    static constexpr int NS = P == 4 ? 2 : (P == 2 ? 3 : 4);     // sized so that two CTAs fit an SM in every mode
+    static constexpr int NS = P == 4 ? 2 : (P == 2 ? 4 : 6);
     float A[KA][TM];
     float W[NS][KC][FN_H];
     float pos[3][TM];
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) siren_exact_kernel(ExactArgs a) {
 // rarely come near zero) take 16-point tiles -- lowest latency per tile, one wave as long as the list fits
 // 16 x gridDim points -- longer ones 32-point tiles, which keep it to one wave up to twice that and do twice the FFMA
 // per weight slab fetched from L2.
-__global__ void __launch_bounds__(NTHREADS, 2) siren_exact_guard_kernel(ExactArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) siren_exact_guard_kernel(ExactArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_only = *a.n_only_dev;
     if (n_only <= 16 * (int)gridDim.x) siren_exact_body<true, 1>(a, smem_raw);
@@ -418,11 +418,10 @@ int guard_refine(const FnLayout& L, const unsigned char* packed, const float* po
     a.guard_stats = stats;
     // (stats[0..2] were zeroed and stats[3] = tau written by guard_scan_kernel's launch above: no host memory is
     // touched here, so the whole refinement can sit inside a captured CUDA graph)
-    // two CTAs per SM (the tiles are latency-bound on their weight slabs: two of them interleave on one SM); tile size
-    // chosen on the device from the list length
+    // one CTA per SM (118 / 140 KB of shared memory); tile size chosen on the device from the list length
     size_t smem = sizeof(Smem<2>) > sizeof(Smem<1>) ? sizeof(Smem<2>) : sizeof(Smem<1>);
     FN_CUDA_OK(cudaFuncSetAttribute(siren_exact_guard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    siren_exact_guard_kernel<<<num_sms() * 2, NTHREADS, smem, st>>>(a);
+    siren_exact_guard_kernel<<<num_sms(), NTHREADS, smem, st>>>(a);
     FN_LAUNCH_OK("siren_exact_kernel(guard)");
     return 0;
 }

@@ -100,6 +100,15 @@ struct Fast3Args {
     long long* trace;
 };
 
+// timing experiments (wrong results): FENERF_B200_DEBUG_SHORT_LOADS is a bit mask in builds with -DFENERF_DEBUG_SHORT_LOADS
+//   1 short weight loads   2 FiLM epilogue does nothing but the hand-offs   4 no tcgen05.mma (commits only)
+//   8 no sin   16 no activation stores   32 no tcgen05.ld
+#ifdef FENERF_DEBUG_SHORT_LOADS
+#define FN_DBG(bit) (a.debug_short_loads & (bit))
+#else
+#define FN_DBG(bit) 0
+#endif
+
 template <bool kTrace>
 #ifdef FENERF_AB_MAXNREG
 __global__ void __maxnreg__(FENERF_AB_MAXNREG) siren_fast3_kernel(const __grid_constant__ Fast3Args a) {
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                 if ((int)(it % RING) != warp) continue;
                                 const LoadOp op = s_loads[li + j];          // before the wait: off the turnaround path
                                 uint32_t bytes = (uint32_t)op.bytes16 * 16u;
-                                if (a.debug_short_loads) bytes = 1024u;     // timing experiment only: wrong results
+                                if (FN_DBG(1)) bytes = 1024u;               // timing experiment only: wrong results
                                 const unsigned char* src = a.packed + op.src;
                                 mbar_wait(bar_empty + 8 * warp, (uses & 1) ^ 1);
                                 ++uses;
@@ -278,6 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                                 if (jj == 0) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
                                                 tc_fence_after();
                                             }
+                                            if (!FN_DBG(4))
                                             tc_mma_f16_elect(d0 + (jj & 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kSlot16 + c * kChunk16 + 2 * k),
                                                              kDescHiMN | (uint64_t)(x_lo0 + ((jj >> 1) * 2 + c) * kChunk16 + 256 * k), idesc,
                                                              ((jj >> 1) == 0 && c == 0 && k == 0) ? 0u : 1u);
@@ -462,23 +472,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         const uint32_t sw = kk & 7u;
                         const float f_h = fr[h], p_h = ph[h];
                         uint32_t r[2][16];
+#ifdef FENERF_DEBUG_SHORT_LOADS
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[0][j] = r[1][j] = 0x3f000000u + (uint32_t)j;
+                        if (!FN_DBG(2)) {
+                        if (!FN_DBG(32))
+#endif
                         tc_ld16(t_lane + h * 128, r[0]);
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {          // 128 points: 8 groups of 16
+#ifdef FENERF_DEBUG_SHORT_LOADS
+                            if (!FN_DBG(32)) {
+                                tc_wait_ld();
+                                if (g < 7) tc_ld16(t_lane + h * 128 + (g + 1) * 16, r[(g + 1) & 1]);
+                            }
+#else
                             tc_wait_ld();
                             if (g < 7) tc_ld16(t_lane + h * 128 + (g + 1) * 16, r[(g + 1) & 1]);
+#endif
 #pragma unroll
                             for (int j8 = 0; j8 < 2; ++j8) {
                                 float v[8];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = __sinf(fmaf(f_h, __uint_as_float(r[g & 1][j8 * 8 + j]), p_h));
+                                for (int j = 0; j < 8; ++j) {
+                                    const float u = fmaf(f_h, __uint_as_float(r[g & 1][j8 * 8 + j]), p_h);
+                                    v[j] = FN_DBG(8) ? u : __sinf(u);
+                                }
                                 uint4 pk;
                                 pk.x = pack_half2(v[0], v[1]); pk.y = pack_half2(v[2], v[3]);
                                 pk.z = pack_half2(v[4], v[5]); pk.w = pack_half2(v[6], v[7]);
                                 const uint32_t pt8 = (uint32_t)(g * 2 + j8);             // which group of 8 points (0..15)
+                                if (!FN_DBG(16) || pk.x == 0x12345678u)
                                 *reinterpret_cast<uint4*>(rowp + (pt8 >> 3) * 1024u + (((pt8 & 7u) ^ sw) << 4)) = pk;
                             }
                         }
+#ifdef FENERF_DEBUG_SHORT_LOADS
+                        }
+#endif
                         // chunks 2h, 2h+1 written, accumulator half h drained
                         if (h == 0) tr.log('H', tl, s, 0);
                         fence_async_smem();
@@ -674,7 +704,7 @@ int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const flo
 #ifdef FENERF_DEBUG_SHORT_LOADS
     {   // profiling aid (tools/diag_fast.py), wrong results by design: only in builds that define the macro
         const char* e = getenv("FENERF_B200_DEBUG_SHORT_LOADS");
-        a.debug_short_loads = (e && atoi(e)) ? 1 : 0;
+        a.debug_short_loads = e ? atoi(e) : 0;
         if (a.debug_short_loads) fprintf(stderr, "fenerf_b200: FENERF_B200_DEBUG_SHORT_LOADS set -- RESULTS ARE WRONG (timing experiment)\n");
     }
 #endif
