@@ -41,7 +41,13 @@ constexpr int TILE = 128;
 constexpr int RING = 3;
 constexpr int MMA_WARP = RING;                       // issuer of tile X; MMA_WARP + 1 issues tile Y
 constexpr int EPI_WARP0 = RING + 2;
-constexpr int NTHREADS = (EPI_WARP0 + 8) * 32;      // 416
+#ifdef FENERF_AB_EPI4
+constexpr int EPI_SPLIT = 1;                         // epilogue warps per TMEM lane quadrant and tile
+#else
+constexpr int EPI_SPLIT = 2;                         // two: each takes 64 of the tile's 128 points in the FiLM epilogues
+#endif
+constexpr int EPI_WARPS = 4 * EPI_SPLIT;             // per tile
+constexpr int NTHREADS = (EPI_WARP0 + 2 * EPI_WARPS) * 32;      // 672
 constexpr uint32_t CHUNK_BYTES = 16384;
 constexpr uint32_t STAGE_BYTES = 32768;
 constexpr uint32_t TILE_SMEM = 4 * CHUNK_BYTES;      // four activation chunks per tile
@@ -52,6 +58,11 @@ constexpr uint32_t SMEM_TOTAL = SMEM_TAB + 96 * 16 + 24 * 8;     // 231360
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_LOADS = 96;
 constexpr int MAX_STAGES = 24;
+#ifdef FENERF_AB_LD32
+constexpr int GW = 32;                               // TMEM columns per tcgen05.ld in the FiLM epilogue
+#else
+constexpr int GW = 16;
+#endif
 
 enum : uint8_t { EPI_FILM = 0, EPI_HEAD_TRUNK = 1, EPI_HEAD_RGB = 2 };
 enum : uint8_t { X_NONE = 0, X_POS = 1, X_EXTRA = 2 };   // load reads the K-major input slots instead of an activation chunk
@@ -95,16 +106,15 @@ struct Fast3Args {
     float* sigma_out;      // optional compact copy of the density channel, one float per point (the resampler's input)
     long long ppb, tiles_per_batch, n_tiles;
     int dir_group, lock_dirs;
-    int debug_short_loads;
     int sigma_only;        // the program stops after the trunk head; only out[..., C-1] is written
     long long* trace;
 };
 
-// timing experiments (wrong results): FENERF_B200_DEBUG_SHORT_LOADS is a bit mask in builds with -DFENERF_DEBUG_SHORT_LOADS
-//   1 short weight loads   2 FiLM epilogue does nothing but the hand-offs   4 no tcgen05.mma (commits only)
-//   8 no sin   16 no activation stores   32 no tcgen05.ld
-#ifdef FENERF_DEBUG_SHORT_LOADS
-#define FN_DBG(bit) (a.debug_short_loads & (bit))
+// Timing experiments (WRONG results by design; tools/ablate_fast3.sh): -DFENERF_ABLATE=<mask> builds a variant without
+//   1 the weight bytes (1 KB loads)   2 the FiLM epilogue's work (hand-offs only)   4 tcgen05.mma (commits only)
+//   8 sin   16 the activation stores   32 tcgen05.ld
+#ifdef FENERF_ABLATE
+#define FN_DBG(bit) ((FENERF_ABLATE) & (bit))
 #else
 #define FN_DBG(bit) 0
 #endif
@@ -117,7 +127,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
 #endif
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a lane-0 broadcast: the compiler then knows it (and every ring / descriptor address derived
+    // from the role and tile index) is warp-uniform and keeps the issuer's operand math in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t bar_full = sbase + SMEM_BAR;             // [RING][2]: slot filled with a load of tile t (each issuer
                                                             // only ever waits on its own tile's barriers, in order)
     const uint32_t bar_empty = bar_full + 16 * RING;        // [RING]
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         for (int t = 0; t < 2; ++t) {
             for (int h = 0; h < 2; ++h) {
                 mbar_init(bar_acc + 8 * (t * 2 + h), 1);
-                mbar_init(bar_aready + 8 * (t * 2 + h), 4);
+                mbar_init(bar_aready + 8 * (t * 2 + h), EPI_WARPS);
             }
             mbar_init(bar_xmain + 8 * t, 1);
             mbar_init(bar_xready + 8 * t, 4);
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         // so the ~1000 cycles of commit / barrier latency between two phases of one tile overlap with the
         // other issuer's MMAs instead of idling the tensor pipe.
         const int t = warp - MMA_WARP;
-        uint32_t used[RING] = {0, 0, 0};            // per-slot use counts of THIS tile (phase parity of full[slot][t])
+        uint32_t full_par = 0;                      // bit s: phase parity of full[s][t] this tile waits for next
         uint32_t it = 0;                            // global load number (slot = it % RING), as in the producers
         uint32_t n_ready = 0, n_x = 0;
         Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, t == 0 ? 1 : 0);
@@ -206,10 +218,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
         // one ring slot's "full" wait for a single-load step (slot number is a runtime value here)
         auto wait_full = [&](uint32_t slot) {
-            const uint32_t cnt = slot == 0 ? used[0] : slot == 1 ? used[1] : used[2];
-            mbar_wait(bar_full + 16 * slot + 8 * t, cnt & 1);
+            mbar_wait(bar_full + 16 * slot + 8 * t, (full_par >> slot) & 1u);
             tc_fence_after();
-            if (slot == 0) ++used[0]; else if (slot == 1) ++used[1]; else ++used[2];
+            full_par ^= 1u << slot;
         };
         // stage flags as register bit masks: a phase change costs no memory access
         uint32_t m_uniform = 0, m_xsync = 0, m_fuse = 0;
@@ -264,48 +275,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             ++it;
                         };
                         if (st_uniform) {
-                            // straight-line: 4 rounds x 8 MMAs, [h0 k01][h1 k01][h0 k23][h1 k23], in ring slots
-                            // s0, s0+1, s0+2, s0 (mod 3); one unrolled copy per starting slot so that every
-                            // descriptor word is a base plus an immediate
-                            auto issue = [&](auto s0_tag) {
-                                constexpr int S0 = decltype(s0_tag)::value;
-                                constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);      // B (activations) MN-major
-                                mbar_wait(bar_full + 16 * S0 + 8 * t, used[S0] & 1);
-                                tc_fence_after();
+                            // 4 rounds x 8 MMAs, [h0 k01][h1 k01][h0 k23][h1 k23], in ring slots s0, s0+1, s0+2, s0 (mod 3).
+                            // One compact loop for every starting slot and both issuers: the fully unrolled
+                            // per-slot copies of round 1 were ~77 KB of straight-line code that each issuer
+                            // walked once per stage.
+                            constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);          // B (activations) MN-major
+                            uint32_t slot = it % RING;
+#pragma unroll 1
+                            for (int jj = 0; jj < 4; ++jj) {
+                                // the [h1 k01] round needs accumulator half 1 drained (and, later, chunks 2,3)
+                                if (jj == 1) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
+                                wait_full(slot);
+                                tr.log('F', tl, ss, t * 64 + jj);
+                                const uint32_t w_lo = ring_lo + slot * kSlot16;
+                                const uint32_t x_lo = x_lo0 + (uint32_t)(jj >> 1) * 2u * kChunk16;
+                                const uint32_t d = d0 + (uint32_t)(jj & 1) * 128u;
 #pragma unroll
-                                for (int jj = 0; jj < 4; ++jj) {
-                                    const int slot = (S0 + jj) % RING;
-                                    tr.log('F', tl, ss, t * 64 + jj);
+                                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k) {
-                                            if (c == 1 && k == 0 && jj < 3) {   // next slot's wait overlaps this slot's MMAs
-                                                const int ns = (S0 + jj + 1) % RING;
-                                                mbar_wait(bar_full + 16 * ns + 8 * t, (used[ns] + (jj + 1 >= RING ? 1 : 0)) & 1);
-                                                // the [h1 k01] round needs accumulator half 1 drained (and, later, chunks 2,3)
-                                                if (jj == 0) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
-                                                tc_fence_after();
-                                            }
-                                            if (!FN_DBG(4))
-                                            tc_mma_f16_elect(d0 + (jj & 1) * 128, kDescHi | (uint64_t)(ring_lo + slot * kSlot16 + c * kChunk16 + 2 * k),
-                                                             kDescHiMN | (uint64_t)(x_lo0 + ((jj >> 1) * 2 + c) * kChunk16 + 256 * k), idesc,
-                                                             ((jj >> 1) == 0 && c == 0 && k == 0) ? 0u : 1u);
-                                        }
-                                    tc_commit_elect(bar_empty + 8 * slot);
-                                    // first colour layer: chunks 0/1 have been read for the last time once [h0 k01] and
-                                    // [h1 k01] retire; the epilogue overwrites chunk 0 with the extra input slots while
-                                    // the k23 rounds run
-                                    if (jj == 1 && st_xsync) tc_commit_elect(bar_xmain + 8 * t);
-                                    // half 0 is complete after [h0 k23] (and chunks 0,1 were last read by [h1 k01])
-                                    if (jj == 2 && !st_xsync) tc_commit_elect(bar_acc + 8 * (t * 2));
-                                }
-                                used[S0] += 2; used[(S0 + 1) % RING] += 1; used[(S0 + 2) % RING] += 1;
-                            };
-                            const uint32_t s0 = it % RING;
-                            if (s0 == 0) issue(std::integral_constant<int, 0>{});
-                            else if (s0 == 1) issue(std::integral_constant<int, 1>{});
-                            else issue(std::integral_constant<int, 2>{});
+                                    for (int k = 0; k < 4; ++k)
+                                        if (!FN_DBG(4))
+                                            tc_mma_f16_elect(d, kDescHi | (uint64_t)(w_lo + c * kChunk16 + 2 * k),
+                                                             kDescHiMN | (uint64_t)(x_lo + c * kChunk16 + 256 * k), idesc,
+                                                             (jj < 2 && c == 0 && k == 0) ? 0u : 1u);
+                                tc_commit_elect(bar_empty + 8 * slot);
+                                tr.log('I', tl, ss, t * 64 + jj);
+                                // first colour layer: chunks 0/1 have been read for the last time once [h0 k01] and
+                                // [h1 k01] retire; the epilogue overwrites chunk 0 with the extra input slots while
+                                // the k23 rounds run
+                                if (jj == 1 && st_xsync) tc_commit_elect(bar_xmain + 8 * t);
+                                // half 0 is complete after [h0 k23] (and chunks 0,1 were last read by [h1 k01])
+                                if (jj == 2 && !st_xsync) tc_commit_elect(bar_acc + 8 * (t * 2));
+                                slot = slot + 1 == RING ? 0u : slot + 1;
+                            }
                             it += 4;
                             if (st_xsync) {
                                 // wait until the epilogue has written the extra input slots into chunk 0
@@ -346,7 +348,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         }
     } else {
         // ================= epilogue warps =================
-        const int t = (warp - EPI_WARP0) >> 2;         // which tile of the pair
+        const int t = (warp - EPI_WARP0) / EPI_WARPS;  // which tile of the pair
+        const int j = ((warp - EPI_WARP0) >> 2) % EPI_SPLIT;   // which 128 / EPI_SPLIT points of the tile in the FiLM epilogues;
+                                                       // everything per point (input slots, heads) is done by the j == 0 warps
         const int q = warp & 3;                        // TMEM lane quadrant (hardware: warp id % 4)
         const int row = q * 32 + lane;                 // feature within a half (FiLM) / point (heads, input slots)
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         const float* label_w = reinterpret_cast<const float*>(a.packed + L.label_w);
         uint32_t n_acc = 0, n_x = 0;
         // traced: quadrant-0 warp of each tile (roles 2, 3); roles 1 / 0 are the issuers of tile X / Y
-        Tracer<kTrace> tr(q == 0 && lane == 0 ? a.trace : nullptr, 2 + t);
+        Tracer<kTrace> tr(q == 0 && j == 0 && lane == 0 ? a.trace : nullptr, 2 + t);
         int tl = 0;
         // position (already box-warped) and view direction of this thread's point in tile `tile_i`; zeros past the end
         auto load_inputs = [&](long long tile_i, float (&pos)[3], float (&dir)[3]) {
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
             // ---- input slots of this thread's point (layout.h): positions now (chunk 3), direction + grid
             //      features kept in registers until the first colour layer ----
             uint4 xslots[8];
-            {
+            if (j == 0) {
                 float pos[3], dir[3];
                 if (have_next) {
 #pragma unroll
@@ -422,11 +426,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                 }
                 const uint4* src = reinterpret_cast<const uint4*>(slots);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) xslots[j] = src[j];
+                for (int i = 0; i < 8; ++i) xslots[i] = src[i];
                 // positions: K-step 0 = pieces 0,1 of the row, into activation chunk 3 (free at tile start)
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    *reinterpret_cast<uint4*>(tsm + 3 * CHUNK_BYTES + xrow_off + (((uint32_t)j ^ xsw) << 4)) = xslots[j];
+                for (int i = 0; i < 2; ++i)
+                    *reinterpret_cast<uint4*>(tsm + 3 * CHUNK_BYTES + xrow_off + (((uint32_t)i ^ xsw) << 4)) = xslots[i];
             }
             fence_async_smem();
             tc_fence_before();
@@ -447,14 +451,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         fr[h] = __ldg(film_l + h * 128 + fl);
                         ph[h] = fmaf(fr[h], __ldg(bias + h * 128 + fl), __ldg(film_l + FN_H + h * 128 + fl));
                     }
-                    if (sop.xsync) {
+                    if (sop.xsync && j == 0) {
                         // first colour layer: once its main MMAs have retired, chunk 0 takes the K-major extra
                         // input slots (pieces 2..7 of the row = direction and grid features)
                         mbar_wait(my_xmain, n_x & 1);
                         tc_fence_after();
 #pragma unroll
-                        for (int j = 2; j < 8; ++j)
-                            *reinterpret_cast<uint4*>(tsm + xrow_off + (((uint32_t)j ^ xsw) << 4)) = xslots[j];
+                        for (int i = 2; i < 8; ++i)
+                            *reinterpret_cast<uint4*>(tsm + xrow_off + (((uint32_t)i ^ xsw) << 4)) = xslots[i];
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(my_xready);
@@ -471,44 +475,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         unsigned char* rowp = tsm + (uint32_t)(h * 2 + (fl >> 6)) * CHUNK_BYTES + (kk >> 3) * 2048u + (kk & 7u) * 128u;
                         const uint32_t sw = kk & 7u;
                         const float f_h = fr[h], p_h = ph[h];
-                        uint32_t r[2][16];
-#ifdef FENERF_DEBUG_SHORT_LOADS
+                        uint32_t r[2][GW];
+                        constexpr int NG = 128 / GW / EPI_SPLIT;             // groups of GW TMEM columns (= points) per warp
+                        const uint32_t col0 = (uint32_t)(j * (128 / EPI_SPLIT));
+                        if (FN_DBG(2 | 32)) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) r[0][j] = r[1][j] = 0x3f000000u + (uint32_t)j;
+                            for (int i = 0; i < GW; ++i) r[0][i] = r[1][i] = 0x3f000000u + (uint32_t)(i + lane);
+                        }
                         if (!FN_DBG(2)) {
-                        if (!FN_DBG(32))
-#endif
-                        tc_ld16(t_lane + h * 128, r[0]);
+                        if (!FN_DBG(32)) tc_ld(t_lane + h * 128 + col0, r[0]);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {          // 128 points: 8 groups of 16
-#ifdef FENERF_DEBUG_SHORT_LOADS
+                        for (int g = 0; g < NG; ++g) {
                             if (!FN_DBG(32)) {
                                 tc_wait_ld();
-                                if (g < 7) tc_ld16(t_lane + h * 128 + (g + 1) * 16, r[(g + 1) & 1]);
+                                if (g + 1 < NG) tc_ld(t_lane + h * 128 + col0 + (g + 1) * GW, r[(g + 1) & 1]);
                             }
-#else
-                            tc_wait_ld();
-                            if (g < 7) tc_ld16(t_lane + h * 128 + (g + 1) * 16, r[(g + 1) & 1]);
-#endif
 #pragma unroll
-                            for (int j8 = 0; j8 < 2; ++j8) {
+                            for (int j8 = 0; j8 < GW / 8; ++j8) {
                                 float v[8];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float u = fmaf(f_h, __uint_as_float(r[g & 1][j8 * 8 + j]), p_h);
-                                    v[j] = FN_DBG(8) ? u : __sinf(u);
+                                for (int i = 0; i < 8; ++i) {
+                                    const float u = fmaf(f_h, __uint_as_float(r[g & 1][j8 * 8 + i]), p_h);
+                                    v[i] = FN_DBG(8) ? u : __sinf(u);
                                 }
                                 uint4 pk;
                                 pk.x = pack_half2(v[0], v[1]); pk.y = pack_half2(v[2], v[3]);
                                 pk.z = pack_half2(v[4], v[5]); pk.w = pack_half2(v[6], v[7]);
-                                const uint32_t pt8 = (uint32_t)(g * 2 + j8);             // which group of 8 points (0..15)
+                                // which group of 8 points (0..15): 64-point atoms are 1024 B apart, 16-byte pieces swizzled inside
+                                const uint32_t pt8 = (col0 >> 3) + (uint32_t)(g * (GW / 8) + j8);
                                 if (!FN_DBG(16) || pk.x == 0x12345678u)
-                                *reinterpret_cast<uint4*>(rowp + (pt8 >> 3) * 1024u + (((pt8 & 7u) ^ sw) << 4)) = pk;
+                                    *reinterpret_cast<uint4*>(rowp + (pt8 >> 3) * 1024u + (((pt8 & 7u) ^ sw) << 4)) = pk;
                             }
                         }
-#ifdef FENERF_DEBUG_SHORT_LOADS
                         }
-#endif
                         // chunks 2h, 2h+1 written, accumulator half h drained
                         if (h == 0) tr.log('H', tl, s, 0);
                         fence_async_smem();
@@ -518,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     }
                     ++n_acc;
                 } else {
-                    if (last) {
+                    if (last && j == 0) {
                         // the inputs of this thread's next point: requested now, consumed at the next tile start
                         const long long ntile = (pair + gridDim.x) * 2 + t;
                         have_next = ntile < a.n_tiles;
@@ -529,7 +528,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     ++n_acc;
                     tc_fence_after();
                     tr.log('W', tl, s, 0);
-                    if (sop.epi == EPI_HEAD_TRUNK) {
+                    if (j != 0) {
+                        // heads are per point: the j == 0 warps own them; the others only keep the hand-off protocol
+                    } else if (sop.epi == EPI_HEAD_TRUNK) {
                         if (L.label_dim > 0) {
                             uint32_t r[32];
                             tc_ld32(t_lane, r);
@@ -701,12 +702,8 @@ int siren_points_fast3(const FnLayout& L, const unsigned char* packed, const flo
     a.L = L; a.packed = packed; a.points = points; a.dirs = dirs; a.film = film; a.out = out; a.sigma_out = sigma_out;
     a.ppb = ppb; a.tiles_per_batch = (ppb + TILE - 1) / TILE; a.n_tiles = a.tiles_per_batch * batch;
     a.dir_group = dir_group < 1 ? 1 : dir_group; a.lock_dirs = lock_dirs; a.trace = trace;
-#ifdef FENERF_DEBUG_SHORT_LOADS
-    {   // profiling aid (tools/diag_fast.py), wrong results by design: only in builds that define the macro
-        const char* e = getenv("FENERF_B200_DEBUG_SHORT_LOADS");
-        a.debug_short_loads = e ? atoi(e) : 0;
-        if (a.debug_short_loads) fprintf(stderr, "fenerf_b200: FENERF_B200_DEBUG_SHORT_LOADS set -- RESULTS ARE WRONG (timing experiment)\n");
-    }
+#ifdef FENERF_ABLATE
+    fprintf(stderr, "fenerf_b200: built with FENERF_ABLATE=%d -- RESULTS ARE WRONG (timing experiment)\n", (int)(FENERF_ABLATE));
 #endif
     if (a.n_tiles <= 0) return 0;
     FN_REQUIRE(ppb % a.dir_group == 0, "points_per_batch %lld not a multiple of dir_group %d", ppb, a.dir_group);

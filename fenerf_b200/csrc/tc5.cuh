@@ -85,6 +85,8 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&r)[16]) { tc_ld16(taddr, r); }
+__device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&r)[32]) { tc_ld32(taddr, r); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO),

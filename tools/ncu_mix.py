@@ -36,3 +36,12 @@ for h, v in stalls.most_common(10):
 print("--- hottest lines")
 for s, n, addr, src, st in sorted(lines, reverse=True)[:int(sys.argv[2]) if len(sys.argv) > 2 else 25]:
     print("%6.2f%% %s %-90s %s" % (100 * s / max(S, 1), addr[-5:], src, dict(sorted(st.items(), key=lambda kv: -float(kv[1]))[:2])))
+
+for key in ("stall_no_inst", "stall_branch_resolving", "stall_sleep"):
+    cols = [h for h in stall_cols if h.startswith(key)]
+    if not cols:
+        continue
+    print("--- lines with the most %s samples" % key)
+    ranked = sorted(lines, key=lambda l: -sum(float(l[4].get(c, 0) or 0) for c in cols))[:12]
+    for s_, n, addr, src, st in ranked:
+        print("%7d  %s %-80s" % (sum(float(st.get(c, 0) or 0) for c in cols), addr[-5:], src))
