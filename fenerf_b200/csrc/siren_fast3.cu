@@ -38,26 +38,39 @@ namespace {
 using namespace tc5;
 
 constexpr int TILE = 128;
-constexpr int RING = 3;
-constexpr int MMA_WARP = RING;                       // issuer of tile X; MMA_WARP + 1 issues tile Y
-constexpr int EPI_WARP0 = RING + 2;
-#ifdef FENERF_AB_EPI4
-constexpr int EPI_SPLIT = 1;                         // epilogue warps per TMEM lane quadrant and tile
+#ifdef FENERF_AB_SLAB16
+constexpr int SLAB_CHUNKS = 1;                       // 6 slots of 16 KB (a slot recycles after 4 MMAs): measured 2-4 % slower
 #else
-constexpr int EPI_SPLIT = 2;                         // two: each takes 64 of the tile's 128 points in the FiLM epilogues
+constexpr int SLAB_CHUNKS = 2;                       // k-chunks (16 KB each) per ring slot: 3 slots of 32 KB
+#endif
+constexpr int RING = 6 / SLAB_CHUNKS;
+constexpr int PROD = 3;                              // producer warps; producer w serves loads it % PROD == w
+constexpr int MMA_WARP = PROD;                       // issuer of tile X; MMA_WARP + 1 issues tile Y
+constexpr int EPI_WARP0 = PROD + 2;
+#ifdef FENERF_AB_EPI8
+constexpr int EPI_SPLIT = 2;                         // measured: no faster for model A (the epilogue is not latency-bound per warp),
+#else                                                // slower for model B (672 threads cap the kernel at 80 registers)
+constexpr int EPI_SPLIT = 1;                         // epilogue warps per TMEM lane quadrant and tile
 #endif
 constexpr int EPI_WARPS = 4 * EPI_SPLIT;             // per tile
-constexpr int NTHREADS = (EPI_WARP0 + 2 * EPI_WARPS) * 32;      // 672
+constexpr int NTHREADS = (EPI_WARP0 + 2 * EPI_WARPS) * 32;      // 416
 constexpr uint32_t CHUNK_BYTES = 16384;
-constexpr uint32_t STAGE_BYTES = 32768;
+constexpr uint32_t STAGE_BYTES = SLAB_CHUNKS * CHUNK_BYTES;
 constexpr uint32_t TILE_SMEM = 4 * CHUNK_BYTES;      // four activation chunks per tile
 constexpr uint32_t SMEM_RING = 2 * TILE_SMEM;
 constexpr uint32_t SMEM_BAR = SMEM_RING + RING * STAGE_BYTES;   // 229376
 constexpr uint32_t SMEM_TAB = SMEM_BAR + 256;                     // per-tile program: loads, then stages
-constexpr uint32_t SMEM_TOTAL = SMEM_TAB + 96 * 16 + 24 * 8;     // 231360
 constexpr int TMEM_COLS = 512;
-constexpr int MAX_LOADS = 96;
+constexpr int MAX_LOADS = 112;
 constexpr int MAX_STAGES = 24;
+constexpr uint32_t SMEM_TOTAL = SMEM_TAB + MAX_LOADS * 16 + MAX_STAGES * 8;   // 231616 (of 232448)
+// The MMA issuers poll their barriers without the suspend-time hint, and every wait ends in a warp vote
+// (tc5.cuh: mbar_wait_warp_spin).  Measured (tools/ablate_fast3.sh): 2 % faster than the sleeping try_wait -- and with six
+// 16 KB ring slots the hinted try_wait on the ring's transaction barriers produced wrong results from a single tile on
+// (cause not identified; the hinted form stays in use only on the epilogue / producer side, where every configuration
+// passes the parity tests).
+#define FN_CTRL_WAIT mbar_wait_warp_spin
+#define FN_PROD_WAIT mbar_wait
 #ifdef FENERF_AB_LD32
 constexpr int GW = 32;                               // TMEM columns per tcgen05.ld in the FiLM epilogue
 #else
@@ -86,7 +99,7 @@ struct StageOp {
     uint8_t epi;           // EPI_*
     uint8_t film;          // FiLM layer index
     uint8_t n_loads;
-    uint8_t uniform;       // 1: 256x256 FiLM layer = 4 loads (h0 k01, h1 k01, h0 k23, h1 k23) [+ one X_EXTRA load]
+    uint8_t uniform;       // 1: 256x256 FiLM layer = 8 / SLAB_CHUNKS slab loads [+ the X_EXTRA loads]
     uint8_t xsync;         // 1: a fifth, X_EXTRA load follows: before it the issuer commits `xmain` and waits `xready`
     uint8_t l0;            // index of the stage's first load in Fast3Args::loads
     uint8_t fuse_next;     // 1: the issuer runs the next stage of the SAME tile before turning to the other tile
@@ -174,12 +187,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     const FnLayout& L = a.L;
 
-    if (warp < RING) {
+    if (warp < PROD) {
         // ================= weight producers: global load number `it` -> slot it % RING = producer warp it % RING.
         // (Round-robin over ALL loads, not per stage: a slot is then always reused RING loads later, so the
         // first load of a phase was requested two rounds before the previous phase ended.)
         if (lane == 0) {
-            uint32_t it = 0, uses = 0;
+            uint32_t it = 0, empty_par = 0;         // bit s: parity of the next wait on empty[s] (starts "free")
             for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x) {
                 const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
                 for (int s = 0; s < a.n_stages;) {
@@ -189,15 +202,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         for (int ss = s; ss < s_end; ++ss) {
                             const int n = s_stages[ss].n_loads, li = s_stages[ss].l0;
                             for (int j = 0; j < n; ++j, ++it) {
-                                if ((int)(it % RING) != warp) continue;
+                                if ((int)(it % PROD) != warp) continue;
+                                const uint32_t slot = it % RING;
                                 const LoadOp op = s_loads[li + j];          // before the wait: off the turnaround path
                                 uint32_t bytes = (uint32_t)op.bytes16 * 16u;
                                 if (FN_DBG(1)) bytes = 1024u;               // timing experiment only: wrong results
                                 const unsigned char* src = a.packed + op.src;
-                                mbar_wait(bar_empty + 8 * warp, (uses & 1) ^ 1);
-                                ++uses;
-                                mbar_arrive_expect_tx(bar_full + 16 * warp + 8 * t, bytes);
-                                bulk_g2s(sbase + SMEM_RING + warp * STAGE_BYTES, src, bytes, bar_full + 16 * warp + 8 * t);
+                                FN_PROD_WAIT(bar_empty + 8 * slot, ((empty_par >> slot) & 1u) ^ 1u);
+                                empty_par ^= 1u << slot;
+                                mbar_arrive_expect_tx(bar_full + 16 * slot + 8 * t, bytes);
+                                bulk_g2s(sbase + SMEM_RING + slot * STAGE_BYTES, src, bytes, bar_full + 16 * slot + 8 * t);
                             }
                         }
                     s = s_end;
@@ -217,8 +231,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         const uint32_t ring_lo = (sbase + SMEM_RING) >> 4;
         constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
         // one ring slot's "full" wait for a single-load step (slot number is a runtime value here)
+        // Every wait of the issuer ends with a warp vote (mbar_wait_warp): with the operand math in uniform registers ptxas
+        // emits tcgen05.mma / commit as warp-level UTCHMMA / UTCBAR without the elect.sync, and lanes that left a per-thread
+        // try_wait loop one by one issued them once per warp fragment (seen: K-steps accumulated twice).
+        auto ctrl_wait = [&](uint32_t bar, uint32_t parity) { FN_CTRL_WAIT(bar, parity); };
         auto wait_full = [&](uint32_t slot) {
-            mbar_wait(bar_full + 16 * slot + 8 * t, (full_par >> slot) & 1u);
+            ctrl_wait(bar_full + 16 * slot + 8 * t, (full_par >> slot) & 1u);
             tc_fence_after();
             full_par ^= 1u << slot;
         };
@@ -239,15 +257,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     for (int ss = s; ss < s_end; ++ss) {
                         const bool st_uniform = (m_uniform >> ss) & 1u, st_xsync = (m_xsync >> ss) & 1u;
                         if (tt != t) {                       // the other issuer's phase: only the ring position moves
-                            it += st_uniform ? (st_xsync ? 5u : 4u) : 1u;
+                            it += s_stages[ss].n_loads;
                             continue;
                         }
                         tr.log('B', tl, ss, t);
                         const uint32_t rdy_par = n_ready & 1;
                         ++n_ready;
-                        mbar_wait(bar_aready + 8 * (t * 2), rdy_par);
+                        ctrl_wait(bar_aready + 8 * (t * 2), rdy_par);
                         // a plain FiLM layer observes half 1 only before its [h1 k01] round (inside `issue`)
-                        if (!st_uniform) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
+                        if (!st_uniform) ctrl_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
                         tc_fence_after();
                         tr.log('A', tl, ss, t);
                         const uint32_t x_lo0 = (sbase + t * TILE_SMEM) >> 4;      // activation chunk 0 of this tile
@@ -261,8 +279,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             const uint32_t x_lo = x_lo0 + (op.xkind == X_POS ? 3u : 0u) * kChunk16;
                             constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 0);
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const uint32_t w_lo = ring_lo + slot * kSlot16 + (uint32_t)h * (16384u >> 4);
+                            for (int hh = 0; hh < SLAB_CHUNKS; ++hh) {       // a 32 KB slot holds both halves, a 16 KB slot op.half
+                                const uint32_t h = SLAB_CHUNKS == 2 ? (uint32_t)hh : (uint32_t)op.half;
+                                const uint32_t w_lo = ring_lo + slot * kSlot16 + (uint32_t)hh * kChunk16;
 #pragma unroll
                                 for (int k = 0; k < 3; ++k)
                                     if (k < op.nk) {
@@ -275,50 +294,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             ++it;
                         };
                         if (st_uniform) {
-                            // 4 rounds x 8 MMAs, [h0 k01][h1 k01][h0 k23][h1 k23], in ring slots s0, s0+1, s0+2, s0 (mod 3).
-                            // One compact loop for every starting slot and both issuers: the fully unrolled
-                            // per-slot copies of round 1 were ~77 KB of straight-line code that each issuer
-                            // walked once per stage.
+                            // The layer's eight (half, k-chunk) pieces in the order [h0 c0][h0 c1][h1 c0][h1 c1][h0 c2][h0 c3][h1 c2][h1 c3],
+                            // SLAB_CHUNKS of them per ring slot, 4 MMAs each.  One compact loop for every starting slot and both
+                            // issuers (all operand math stays in uniform registers).
                             constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);          // B (activations) MN-major
                             uint32_t slot = it % RING;
 #pragma unroll 1
-                            for (int jj = 0; jj < 4; ++jj) {
-                                // the [h1 k01] round needs accumulator half 1 drained (and, later, chunks 2,3)
-                                if (jj == 1) mbar_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
+                            for (int r = 0; r < 8 / SLAB_CHUNKS; ++r) {
+                                // the first h1 piece needs accumulator half 1 drained (and, later, chunks 2,3)
+                                if (r * SLAB_CHUNKS == 2) ctrl_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
                                 wait_full(slot);
-                                tr.log('F', tl, ss, t * 64 + jj);
-                                const uint32_t w_lo = ring_lo + slot * kSlot16;
-                                const uint32_t x_lo = x_lo0 + (uint32_t)(jj >> 1) * 2u * kChunk16;
-                                const uint32_t d = d0 + (uint32_t)(jj & 1) * 128u;
+                                tr.log('F', tl, ss, t * 64 + r);
 #pragma unroll
-                                for (int c = 0; c < 2; ++c)
+                                for (int cc = 0; cc < SLAB_CHUNKS; ++cc) {
+                                    const uint32_t idx = (uint32_t)(r * SLAB_CHUNKS + cc);
+                                    const uint32_t half = (idx >> 1) & 1u, chunk = (idx >> 2) * 2u + (idx & 1u);
+                                    const uint32_t w_lo = ring_lo + slot * kSlot16 + (uint32_t)cc * kChunk16;
+                                    const uint32_t x_lo = x_lo0 + chunk * kChunk16;
+                                    const uint32_t d = d0 + half * 128u;
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
                                         if (!FN_DBG(4))
-                                            tc_mma_f16_elect(d, kDescHi | (uint64_t)(w_lo + c * kChunk16 + 2 * k),
-                                                             kDescHiMN | (uint64_t)(x_lo + c * kChunk16 + 256 * k), idesc,
-                                                             (jj < 2 && c == 0 && k == 0) ? 0u : 1u);
+                                            tc_mma_f16_elect(d, kDescHi | (uint64_t)(w_lo + 2 * k), kDescHiMN | (uint64_t)(x_lo + 256 * k), idesc,
+                                                             (chunk == 0 && k == 0) ? 0u : 1u);
+                                }
                                 tc_commit_elect(bar_empty + 8 * slot);
-                                tr.log('I', tl, ss, t * 64 + jj);
-                                // first colour layer: chunks 0/1 have been read for the last time once [h0 k01] and
-                                // [h1 k01] retire; the epilogue overwrites chunk 0 with the extra input slots while
-                                // the k23 rounds run
-                                if (jj == 1 && st_xsync) tc_commit_elect(bar_xmain + 8 * t);
-                                // half 0 is complete after [h0 k23] (and chunks 0,1 were last read by [h1 k01])
-                                if (jj == 2 && !st_xsync) tc_commit_elect(bar_acc + 8 * (t * 2));
+                                tr.log('I', tl, ss, t * 64 + r);
+                                const int done = (r + 1) * SLAB_CHUNKS;      // pieces issued so far
+                                // first colour layer: chunks 0/1 have been read for the last time once the k01 pieces
+                                // retire; the epilogue overwrites chunk 0 with the extra input slots while the k23 pieces run
+                                if (done == 4 && st_xsync) tc_commit_elect(bar_xmain + 8 * t);
+                                // half 0 is complete after [h0 c3] (and chunks 0,1 were last read by [h1 c1])
+                                if (done == 6 && !st_xsync) tc_commit_elect(bar_acc + 8 * (t * 2));
                                 slot = slot + 1 == RING ? 0u : slot + 1;
                             }
-                            it += 4;
+                            it += 8 / SLAB_CHUNKS;
                             if (st_xsync) {
                                 // wait until the epilogue has written the extra input slots into chunk 0
-                                mbar_wait(bar_xready + 8 * t, n_x & 1);
+                                ctrl_wait(bar_xready + 8 * t, n_x & 1);
                                 ++n_x;
                                 tc_fence_after();
                                 tr.log('X', tl, ss, t);
-                                x_load(s_loads[s_stages[ss].l0 + 4]);
+                                for (int xl = 0; xl < 2 / SLAB_CHUNKS; ++xl) x_load(s_loads[s_stages[ss].l0 + 8 / SLAB_CHUNKS + xl]);
                             }
                         } else if (s_loads[s_stages[ss].l0].xkind != X_NONE) {
-                            x_load(s_loads[s_stages[ss].l0]);
+                            for (int xl = 0; xl < 2 / SLAB_CHUNKS; ++xl) x_load(s_loads[s_stages[ss].l0 + xl]);
                         } else {
                             // head: activations are the A operand (M = 128 points, MN-major), the [n rows][256] head
                             // image the B operand; 4 k-chunks x 4 K-steps, fully unrolled
@@ -618,17 +638,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
 // ---- host: the per-tile stage / load program ------------------------------------------------------
 LoadOp* push(Fast3Args& A) { LoadOp* op = &A.loads[A.n_loads++]; memset(op, 0, sizeof(*op)); op->n_chunks = 1; op->w_is_a = 1; return op; }
 
-void push_film_pair(Fast3Args& A, size_t img_off, int half, int pair, bool first) {
+// one ring slot of a 256x256 FiLM layer image ([half][k-chunk][16 KB]): SLAB_CHUNKS consecutive k-chunks of one half
+void push_film_slab(Fast3Args& A, size_t img_off, int half, int chunk) {
     LoadOp* op = push(A);
-    op->src = (uint32_t)(img_off + (size_t)half * 65536 + (size_t)pair * STAGE_BYTES);
-    op->bytes16 = STAGE_BYTES / 16; op->x_chunk = (uint8_t)(pair * 2); op->n_chunks = 2; op->k0 = 0; op->nk = 4; op->n8 = TILE / 8;
-    op->half = (uint8_t)half; op->first = first ? 1 : 0;
+    op->src = (uint32_t)(img_off + (size_t)half * 65536 + (size_t)chunk * CHUNK_BYTES);
+    op->bytes16 = STAGE_BYTES / 16; op->x_chunk = (uint8_t)chunk; op->n_chunks = SLAB_CHUNKS; op->k0 = 0; op->nk = 4; op->n8 = TILE / 8;
+    op->half = (uint8_t)half; op->first = chunk == 0 ? 1 : 0;
 }
 
+// the [256 features][64 slots] input image (32 KB, halves 16 KB apart): one load per ring slot
 void push_x(Fast3Args& A, size_t img_off, uint8_t kind, int k0, int nk, bool first) {
-    LoadOp* op = push(A);       // the whole [256 features][64 slots] image, 32 KB: halves 16 KB apart
-    op->src = (uint32_t)img_off; op->bytes16 = 32768 / 16; op->k0 = (uint8_t)k0; op->nk = (uint8_t)nk; op->n8 = TILE / 8;
-    op->first = first ? 1 : 0; op->xkind = kind;
+    for (int h = 0; h < 2 / SLAB_CHUNKS; ++h) {
+        LoadOp* op = push(A);
+        op->src = (uint32_t)(img_off + (size_t)h * CHUNK_BYTES); op->bytes16 = STAGE_BYTES / 16; op->k0 = (uint8_t)k0; op->nk = (uint8_t)nk;
+        op->n8 = TILE / 8; op->half = (uint8_t)h; op->first = first ? 1 : 0; op->xkind = kind;
+    }
 }
 
 void push_head(Fast3Args& A, size_t img_off, int img_rows, int n) {
@@ -662,15 +686,13 @@ bool build_program(const FnLayout& L, Fast3Args& A, bool sigma_only) {
         }
         const bool c0 = (l == L.trunk_hidden);
         int l0 = A.n_loads;
-        push_film_pair(A, L.hid_img[l], 0, 0, true);
-        push_film_pair(A, L.hid_img[l], 1, 0, true);
-        push_film_pair(A, L.hid_img[l], 0, 1, false);
-        push_film_pair(A, L.hid_img[l], 1, 1, false);
+        for (int idx = 0; idx < 8; idx += SLAB_CHUNKS)       // [h0 c0][h0 c1][h1 c0][h1 c1][h0 c2][h0 c3][h1 c2][h1 c3]
+            push_film_slab(A, L.hid_img[l], (idx >> 1) & 1, (idx >> 2) * 2 + (idx & 1));
         if (c0) push_x(A, L.color0_ximg, X_EXTRA, 1, L.grid_channels > 0 ? 3 : 1, false);
         StageOp& st = end_stage(EPI_FILM, (uint8_t)(l + 1), l0);
         st.uniform = 1;
         st.xsync = c0 ? 1 : 0;
-        if (A.n_loads > MAX_LOADS - 8 || A.n_stages > MAX_STAGES - 3) return false;
+        if (A.n_loads > MAX_LOADS - 14 || A.n_stages > MAX_STAGES - 3) return false;
     }
     {
         int l0 = A.n_loads;
