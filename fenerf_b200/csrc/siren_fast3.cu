@@ -515,6 +515,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                 float v[8];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
+                                    // (sin on the FMA pipe -- range reduction in turns + a degree-7 polynomial -- for 2 or 3 of
+                                    // every 8 outputs was measured 8 % / 28 % SLOWER: the epilogue is bound by issue slots and
+                                    // single-warp latency at least as much as by the MUFU pipe)
                                     const float u = fmaf(f_h, __uint_as_float(r[g & 1][j8 * 8 + i]), p_h);
                                     v[i] = FN_DBG(8) ? u : __sinf(u);
                                 }
