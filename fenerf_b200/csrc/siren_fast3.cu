@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             for (int c = 0; c < 4; ++c)
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    tc_mma_f16_elect(d0, kDescHiMN | (uint64_t)(x_lo0 + c * kChunk16 + 256 * k),
+                                    tc_mma_f16_elect(d0 + (uint32_t)op.half * 128u, kDescHiMN | (uint64_t)(x_lo0 + c * kChunk16 + 256 * k),
                                                      kDescHi | (uint64_t)(w_lo + c * w_stride16 + 2 * k), idesc, (c | k) ? 1u : 0u);
                             tc_commit_elect(bar_empty + 8 * slot);
                             ++it;
@@ -546,6 +546,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         have_next = ntile < a.n_tiles;
                         if (have_next) load_inputs(ntile, next_pos, next_dir);
                     }
+                    const bool early_h0 = !last && sop.epi == EPI_HEAD_TRUNK;
+                    if (early_h0) {
+                        // the trunk head's result sits in accumulator half 1: chunks 0,1 and accumulator half 0 stay as the last
+                        // FiLM layer left them, so the colour layer's [h0 k01] round may start without waiting for this epilogue
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(my_aready);
+                    }
                     mbar_wait(my_acc, n_acc & 1);
                     mbar_wait(my_acc + 8, n_acc & 1);
                     ++n_acc;
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     } else if (sop.epi == EPI_HEAD_TRUNK) {
                         if (L.label_dim > 0) {
                             uint32_t r[32];
-                            tc_ld32(t_lane, r);
+                            tc_ld32(t_lane + 128, r);
                             tc_wait_ld();
                             if (valid) {
                                 const float inv_scale = __ldg(label_w + FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL);
@@ -583,7 +590,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             }
                         } else {
                             uint32_t r[8];
-                            tc_ld8(t_lane, r);
+                            tc_ld8(t_lane + 128, r);
                             tc_wait_ld();
                             sig_keep = __uint_as_float(r[0]) + __ldg(sigma_w + FN_H);
                             if (valid && a.sigma_only) a.out[flat * C + (C - 1)] = sig_keep;
@@ -624,7 +631,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(my_aready); mbar_arrive(my_aready + 8); }
+                    if (lane == 0) {
+                        if (sop.epi != EPI_HEAD_TRUNK) mbar_arrive(my_aready);       // (the trunk head arrived on half 0 up front)
+                        mbar_arrive(my_aready + 8);
+                    }
                 }
             }
         }
@@ -658,11 +668,13 @@ void push_x(Fast3Args& A, size_t img_off, uint8_t kind, int k0, int nk, bool fir
     }
 }
 
-void push_head(Fast3Args& A, size_t img_off, int img_rows, int n) {
+// `half`: which 128-column half of the tile's accumulator takes the [128 points][n] result.  The trunk head uses half 1, so
+// that the colour layer's first round ([h0 k01], issued right behind it) does not wait for the head's epilogue.
+void push_head(Fast3Args& A, size_t img_off, int img_rows, int n, int half) {
     LoadOp* op = push(A);
     op->src = (uint32_t)img_off;
     op->bytes16 = (uint16_t)((4 * img_rows * FN_KCHUNK * 2) / 16); op->x_chunk = 0; op->n_chunks = 4; op->k0 = 0; op->nk = 4;
-    op->n8 = (uint8_t)(n / 8); op->half = 0; op->first = 1; op->w_is_a = 0;
+    op->n8 = (uint8_t)(n / 8); op->half = (uint8_t)half; op->first = 1; op->w_is_a = 0;
 }
 
 bool build_program(const FnLayout& L, Fast3Args& A, bool sigma_only) {
@@ -681,7 +693,7 @@ bool build_program(const FnLayout& L, Fast3Args& A, bool sigma_only) {
     for (int l = 0; l < L.n_hidden; ++l) {
         if (l == L.trunk_hidden) {
             int l0 = A.n_loads;
-            push_head(A, L.head_img, 32, L.label_dim > 0 ? 32 : 8);
+            push_head(A, L.head_img, 32, L.label_dim > 0 ? 32 : 8, 1);
             // the head and the first colour layer of a tile are issued back to back: the other tile is in
             // its long epilogue meanwhile, and would otherwise hold the in-order issuer at its own head
             end_stage(EPI_HEAD_TRUNK, 0, l0).fuse_next = sigma_only ? 0 : 1;
@@ -699,7 +711,7 @@ bool build_program(const FnLayout& L, Fast3Args& A, bool sigma_only) {
     }
     {
         int l0 = A.n_loads;
-        push_head(A, L.rgb_img, 8, 8);
+        push_head(A, L.rgb_img, 8, 8, 0);
         end_stage(EPI_HEAD_RGB, 0, l0);
     }
     return true;
