@@ -71,6 +71,7 @@ constexpr uint32_t SMEM_TOTAL = SMEM_TAB + MAX_LOADS * 16 + MAX_STAGES * 8;   //
 // passes the parity tests).
 #define FN_CTRL_WAIT mbar_wait_warp_spin
 #define FN_PROD_WAIT mbar_wait
+#define FN_EPI_WAIT mbar_wait_warp_spin     // epilogue warps wait converged as well (tcgen05.ld is .sync.aligned); +0.5-1 % over the hinted form
 #ifdef FENERF_AB_LD32
 constexpr int GW = 32;                               // TMEM columns per tcgen05.ld in the FiLM epilogue
 #else
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     if (sop.xsync && j == 0) {
                         // first colour layer: once its main MMAs have retired, chunk 0 takes the K-major extra
                         // input slots (pieces 2..7 of the row = direction and grid features)
-                        mbar_wait(my_xmain, n_x & 1);
+                        FN_EPI_WAIT(my_xmain, n_x & 1);
                         tc_fence_after();
 #pragma unroll
                         for (int i = 2; i < 8; ++i)
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     const uint32_t kk = (uint32_t)(fl & 63);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        mbar_wait(my_acc + 8 * h, n_acc & 1);
+                        FN_EPI_WAIT(my_acc + 8 * h, n_acc & 1);
                         tc_fence_after();
                         if (h == 0) tr.log('W', tl, s, 0);
                         // feature f = h*128 + fl -> chunk f/64, row k = f%64 of the MN-major chunk
@@ -553,8 +554,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         __syncwarp();
                         if (lane == 0) mbar_arrive(my_aready);
                     }
-                    mbar_wait(my_acc, n_acc & 1);
-                    mbar_wait(my_acc + 8, n_acc & 1);
+                    FN_EPI_WAIT(my_acc, n_acc & 1);
+                    FN_EPI_WAIT(my_acc + 8, n_acc & 1);
                     ++n_acc;
                     tc_fence_after();
                     tr.log('W', tl, s, 0);
