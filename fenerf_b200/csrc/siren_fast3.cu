@@ -299,11 +299,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             // SLAB_CHUNKS of them per ring slot, 4 MMAs each.  One compact loop for every starting slot and both
                             // issuers (all operand math stays in uniform registers).
                             constexpr uint32_t idesc = umma_idesc_f16(TILE, 0, 1);          // B (activations) MN-major
-                            uint32_t slot = it % RING;
 #pragma unroll 1
                             for (int r = 0; r < 8 / SLAB_CHUNKS; ++r) {
                                 // the first h1 piece needs accumulator half 1 drained (and, later, chunks 2,3)
                                 if (r * SLAB_CHUNKS == 2) ctrl_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
+                                const uint32_t slot = it % RING;
                                 wait_full(slot);
                                 tr.log('F', tl, ss, t * 64 + r);
 #pragma unroll
@@ -320,23 +320,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                                              (chunk == 0 && k == 0) ? 0u : 1u);
                                 }
                                 tc_commit_elect(bar_empty + 8 * slot);
+                                ++it;
                                 tr.log('I', tl, ss, t * 64 + r);
                                 const int done = (r + 1) * SLAB_CHUNKS;      // pieces issued so far
                                 // first colour layer: chunks 0/1 have been read for the last time once the k01 pieces
-                                // retire; the epilogue overwrites chunk 0 with the extra input slots while the k23 pieces run
+                                // retire; the epilogue overwrites chunk 0 with the extra input slots while [h0 c2][h0 c3] run
                                 if (done == 4 && st_xsync) tc_commit_elect(bar_xmain + 8 * t);
-                                // half 0 is complete after [h0 c3] (and chunks 0,1 were last read by [h1 c1])
-                                if (done == 6 && !st_xsync) tc_commit_elect(bar_acc + 8 * (t * 2));
-                                slot = slot + 1 == RING ? 0u : slot + 1;
-                            }
-                            it += 8 / SLAB_CHUNKS;
-                            if (st_xsync) {
-                                // wait until the epilogue has written the extra input slots into chunk 0
-                                ctrl_wait(bar_xready + 8 * t, n_x & 1);
-                                ++n_x;
-                                tc_fence_after();
-                                tr.log('X', tl, ss, t);
-                                for (int xl = 0; xl < 2 / SLAB_CHUNKS; ++xl) x_load(s_loads[s_stages[ss].l0 + 8 / SLAB_CHUNKS + xl]);
+                                if (done == 6) {
+                                    if (st_xsync) {
+                                        // the extra-input MMAs (both halves) go in front of the last h1 pieces, so that half 0 still
+                                        // completes one round before the stage ends and its epilogue overlaps that round
+                                        ctrl_wait(bar_xready + 8 * t, n_x & 1);
+                                        ++n_x;
+                                        tc_fence_after();
+                                        tr.log('X', tl, ss, t);
+                                        for (int xl = 0; xl < 2 / SLAB_CHUNKS; ++xl) x_load(s_loads[s_stages[ss].l0 + 6 / SLAB_CHUNKS + xl]);
+                                    }
+                                    // half 0 is complete after [h0 c3] (and chunks 0,1 were last read by [h1 c1])
+                                    tc_commit_elect(bar_acc + 8 * (t * 2));
+                                }
                             }
                         } else if (s_loads[s_stages[ss].l0].xkind != X_NONE) {
                             for (int xl = 0; xl < 2 / SLAB_CHUNKS; ++xl) x_load(s_loads[s_stages[ss].l0 + xl]);
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             tc_commit_elect(bar_empty + 8 * slot);
                             ++it;
                         }
-                        if (!st_uniform || st_xsync) tc_commit_elect(bar_acc + 8 * (t * 2));
+                        if (!st_uniform) tc_commit_elect(bar_acc + 8 * (t * 2));
                         tc_commit_elect(bar_acc + 8 * (t * 2 + 1));
                         tr.log('C', tl, ss, t);
                     }
@@ -702,9 +704,10 @@ bool build_program(const FnLayout& L, Fast3Args& A, bool sigma_only) {
         }
         const bool c0 = (l == L.trunk_hidden);
         int l0 = A.n_loads;
-        for (int idx = 0; idx < 8; idx += SLAB_CHUNKS)       // [h0 c0][h0 c1][h1 c0][h1 c1][h0 c2][h0 c3][h1 c2][h1 c3]
+        for (int idx = 0; idx < 8; idx += SLAB_CHUNKS) {     // [h0 c0][h0 c1][h1 c0][h1 c1][h0 c2][h0 c3] (extras) [h1 c2][h1 c3]
+            if (c0 && idx == 6) push_x(A, L.color0_ximg, X_EXTRA, 1, L.grid_channels > 0 ? 3 : 1, false);
             push_film_slab(A, L.hid_img[l], (idx >> 1) & 1, (idx >> 2) * 2 + (idx & 1));
-        if (c0) push_x(A, L.color0_ximg, X_EXTRA, 1, L.grid_channels > 0 ? 3 : 1, false);
+        }
         StageOp& st = end_stage(EPI_FILM, (uint8_t)(l + 1), l0);
         st.uniform = 1;
         st.xsync = c0 ? 1 : 0;
