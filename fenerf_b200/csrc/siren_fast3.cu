@@ -412,6 +412,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         bool have_next = false;
         float sig_keep = 0.f;                // density of this thread's point: held from the trunk head to the rgb head so
                                              // that [.., r, g, b, sigma] leaves in 16-byte (C = 4) / 8-byte stores
+        // The [r, g, b, sigma] tail of the point's output row is the tail of a tile: its store is deferred until the NEXT tile's
+        // input slots have been handed to the issuer (the fence in front of that hand-off would wait for the store otherwise).
+        // 16 bytes at once when the row is 16 bytes (C = 4), two 8-byte stores when C is even, scalars otherwise.
+        float4 pend_v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pend_p = nullptr;
+        auto flush_tail = [&]() {
+            if (pend_p == nullptr) return;
+            const uintptr_t ob = reinterpret_cast<uintptr_t>(a.out);
+#ifdef FENERF_AB_SCALAR_STORES
+            if (false) {
+#else
+            if (L.out_dim == 4 && (ob & 15) == 0) {
+#endif
+                *reinterpret_cast<float4*>(pend_p) = pend_v;
+            } else if ((L.out_dim & 1) == 0 && (ob & 7) == 0) {
+                *reinterpret_cast<float2*>(pend_p) = make_float2(pend_v.x, pend_v.y);
+                *reinterpret_cast<float2*>(pend_p + 2) = make_float2(pend_v.z, pend_v.w);
+            } else {
+                pend_p[0] = pend_v.x; pend_p[1] = pend_v.y; pend_p[2] = pend_v.z; pend_p[3] = pend_v.w;
+            }
+            pend_p = nullptr;
+        };
         for (long long pair = blockIdx.x; pair * 2 + t < a.n_tiles; pair += gridDim.x, ++tl) {
             const long long tile = pair * 2 + t;
             const long long b = tile / a.tiles_per_batch;
@@ -459,6 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(my_aready); mbar_arrive(my_aready + 8); }
+            flush_tail();
 
             for (int s = 0; s < a.n_stages; ++s) {
                 const StageOp sop = s_stages[s];
@@ -563,11 +586,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                     tr.log('W', tl, s, 0);
                     if (j != 0) {
                         // heads are per point: the j == 0 warps own them; the others only keep the hand-off protocol
+                        if (!last && sop.epi == EPI_HEAD_TRUNK) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(my_aready + 8);
+                        }
                     } else if (sop.epi == EPI_HEAD_TRUNK) {
                         if (L.label_dim > 0) {
                             uint32_t r[32];
                             tc_ld32(t_lane + 128, r);
                             tc_wait_ld();
+                            if (!last) {      // accumulator half 1 is drained: hand it back before the global stores (their latency
+                                              // would otherwise sit in the colour layer's [h1 k01] round via the MEMBAR of a fence)
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(my_aready + 8);
+                            }
                             if (valid) {
                                 const float inv_scale = __ldg(label_w + FENERF_MAX_LABEL * FN_H + FENERF_MAX_LABEL);
                                 const float* lb = label_w + FENERF_MAX_LABEL * FN_H;
@@ -595,6 +629,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             uint32_t r[8];
                             tc_ld8(t_lane + 128, r);
                             tc_wait_ld();
+                            if (!last) {      // accumulator half 1 is drained: hand it back before the global stores (their latency
+                                              // would otherwise sit in the colour layer's [h1 k01] round via the MEMBAR of a fence)
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(my_aready + 8);
+                            }
                             sig_keep = __uint_as_float(r[0]) + __ldg(sigma_w + FN_H);
                             if (valid && a.sigma_only) a.out[flat * C + (C - 1)] = sig_keep;
                             if (valid && a.sigma_out) a.sigma_out[flat] = sig_keep;
@@ -610,37 +650,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                                 const float x = __uint_as_float(r[o]) + __ldg(rgb_w + 3 * FN_H + o);
                                 c3[o] = __fdividef(1.f, 1.f + __expf(-x));
                             }
-                            // [r, g, b, sigma] is the tail of the point's row: 16 bytes at once when the row is 16 bytes
-                            // (C = 4), two 8-byte stores when C is even, scalars otherwise
-                            float* tail = a.out + flat * C + L.label_dim;
-                            const uintptr_t ob = reinterpret_cast<uintptr_t>(a.out);
-#ifdef FENERF_AB_SCALAR_STORES
-                            if (false) {
-#else
-                            if (C == 4 && (ob & 15) == 0) {
-#endif
-                                *reinterpret_cast<float4*>(tail) = make_float4(c3[0], c3[1], c3[2], sig_keep);
-                            } else if ((C & 1) == 0 && (ob & 7) == 0) {
-                                *reinterpret_cast<float2*>(tail) = make_float2(c3[0], c3[1]);
-                                *reinterpret_cast<float2*>(tail + 2) = make_float2(c3[2], sig_keep);
-                            } else {
-                                tail[0] = c3[0]; tail[1] = c3[1]; tail[2] = c3[2]; tail[3] = sig_keep;
-                            }
+                            pend_v = make_float4(c3[0], c3[1], c3[2], sig_keep);
+                            pend_p = a.out + flat * C + L.label_dim;
                         }
                     }
                 }
                 tr.log('D', tl, s, 0);
-                if (!last && sop.epi != EPI_FILM) {
-                    fence_async_smem();
+                if (!last && sop.epi != EPI_FILM && sop.epi != EPI_HEAD_TRUNK) {      // (the trunk head hands both halves back itself)
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) {
-                        if (sop.epi != EPI_HEAD_TRUNK) mbar_arrive(my_aready);       // (the trunk head arrived on half 0 up front)
-                        mbar_arrive(my_aready + 8);
-                    }
+                    if (lane == 0) { mbar_arrive(my_aready); mbar_arrive(my_aready + 8); }
                 }
             }
         }
+        flush_tail();
     }
     // ---- teardown ----
     tc_fence_before();
