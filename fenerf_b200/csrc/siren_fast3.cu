@@ -1,30 +1,36 @@
 // Point network, FAST mode (tcgen05), third-generation kernel: two tiles per CTA, three 32 KB ring slots.
 //
-// What the measurements of round 1 say
-// (profiles/r01_*.txt): per 128-point layer-tile the tensor pipe, the MUFU pipe
-// and the TMEM->register path each need ~2048 cycles, a layer is a dependency chain
-// MMA -> epilogue -> MMA, a ring slot's turnaround is ~1800 cycles whatever its size, and the MMA
-// issuer pays ~400 cycles of barrier/commit bookkeeping per ring round.  Hence:
+// What the measurements say (round 1: profiles/r01_*.txt; round 2: profiles/r02_fast3_ablation.txt, r02_microbench.txt,
+// DESIGN.md section 5): per 128-point layer-tile the tensor pipe needs 2048 cycles (32 MMAs at the measured 64 cycles) and
+// the epilogue ~2300-3500 (one sin per output element: MUFU.SIN is 8 cycles per warp instruction and sub-partition, the fp16
+// pack shares that pipe, and a lone warp per sub-partition only reaches 13.7 cycles per element; two reach 10.3); a layer
+// is a dependency chain MMA -> epilogue -> MMA; a ring slot's turnaround is ~1500 cycles.  Hence:
 //   * TWO tiles per CTA (one CTA per SM) run the same layer program, each with its own MMA-issuer warp
-//     and its own four epilogue warps, so one tile's epilogue (MUFU + TMEM reads) and the ~1000 cycles
-//     an in-order issuer spends between two of its phases overlap the other tile's MMAs;
+//     and its own four epilogue warps, so one tile's epilogue overlaps the other tile's MMAs;
 //   * ring slots are 32 KB = two k-chunks of one feature half = 8 MMAs = 512 tensor cycles per
-//     barrier round; three slots (96 KB in flight), reused in global round-robin over both tiles' loads;
+//     barrier round; three slots (96 KB in flight), reused in global round-robin over both tiles' loads
+//     (six 16 KB slots: measured 2-4 % slower);
 //   * per layer the rounds run [h0 k01][h1 k01][h0 k23][h1 k23] and accumulator / operand hand-offs are
 //     per feature half: half 0 is committed after round 3 (its epilogue overlaps round 4) and the next
 //     layer's first round only needs half 0 of the previous epilogue;
 //   * that ring only fits because the per-tile 16 KB input chunk is gone: the position slots of the
 //     first layer live in activation chunk 3 (free at tile start), and the view-direction / grid
 //     feature slots of the first colour layer are written into activation chunk 0 once that layer's
-//     k01 rounds have retired (the k23 rounds cover the round trip);
+//     k01 rounds have retired; their MMAs go in front of the last round, so half 0 still completes a round early;
 //   * activations are MN-major (points contiguous), so the feature-per-thread epilogue stores 16
-//     bytes at a time; TMEM is drained in 16-column double-buffered pieces;
-//   * the trunk head and the first colour layer of a tile are issued back to back (the other tile is in
-//     a long epilogue then), every stage kind has an unrolled issue path, and the next tile's point
-//     inputs are requested during the previous tile's last stage.
+//     bytes at a time; TMEM is drained in 16-column double-buffered pieces (a tcgen05.ld + wait is ~21 cycles);
+//   * the trunk head and the first colour layer of a tile are issued back to back, the head accumulating into
+//     half 1 so that the colour layer's first round does not wait for the head's epilogue; the head hands its
+//     accumulator back before its global stores, and a tile's last [r, g, b, sigma] store is deferred past the next
+//     tile's hand-off (a fence.proxy.async is a MEMBAR: it would wait for those stores);
+//   * [r2] the warp index comes from a lane-0 shuffle: the compiler then keeps every descriptor / barrier address of
+//     the issuers in uniform registers (6 instead of 18 instructions per MMA, no R2UR / ELECT): -5 % kernel time.
+//     With that, tcgen05.mma / commit become warp-level UTCHMMA / UTCBAR and every wait in front of them must END
+//     CONVERGED (mbar_wait_warp_spin: the loop exit is a warp vote);
+//   * [r2] issuers and epilogue warps poll without the suspend-time hint (+2 %).
 //
-//   warps 0..2    weight producers (one per ring slot)
-//   warps 3, 4    MMA issuers of tile X / tile Y (warp-converged, elect.sync)
+//   warps 0..2    weight producers (producer w serves ring loads it % 3 == w)
+//   warps 3, 4    MMA issuers of tile X / tile Y (warp-converged, uniform-register operands)
 //   warps 5..8    epilogue of tile X      warps 9..12   epilogue of tile Y
 #include "common.cuh"
 #include "siren_common.cuh"
