@@ -403,7 +403,7 @@ def measure_train_step(args, world, rank, local):
                         "1 differentiable render + backward per split, Adam step; synthetic loss (fixed projection of the frames)"
                         % (MODEL_NAME["B"], R, R, S, S, BATCH, SPLIT, BATCH // SPLIT),
             "ms_per_iteration": ms, "faces_rendered_per_iteration": 3 * BATCH, "rendered_faces_per_s": 3 * BATCH / (ms / 1e3),
-            "iterations_per_s": 1e3 / ms, "backward": "fenerf_b200/backward.py (CUDA kernels + library GEMMs), fp16 streams"}
+            "iterations_per_s": 1e3 / ms, "backward": "fenerf_b200/backward.py (CUDA kernels + the library's tcgen05 GEMMs, csrc/gemm5.cu), fp16 streams"}
 
 
 def run_ours(args, world, rank, local):
