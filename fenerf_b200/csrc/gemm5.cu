@@ -73,7 +73,9 @@ constexpr uint32_t NT_SMEM = NT_FILM + 3 * 256 * 4;
 __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_constant__ NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index by lane-0 broadcast: descriptor / barrier arithmetic of the issuer then stays in uniform registers (see
+    // siren_fast3.cu); every wait below is therefore the vote-terminated form, which leaves the warp converged
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t bar_b = sbase + NT_BAR;
     const uint32_t bar_accfull = bar_b + 8 /* [2] */, bar_accempty = bar_b + 24 /* [2] */;
     const uint32_t bar_afull = bar_b + 40 /* [NT_RING] */, bar_aempty = bar_afull + 8 * NT_RING /* [NT_RING] */;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
             const long long m0 = t * 128;
             for (int kc = 0; kc < n_chunks; ++kc, ++ch) {
                 const uint32_t slot = ch % NT_RING, use = ch / NT_RING;
-                mbar_wait(bar_aempty + 8 * slot, (use & 1) ^ 1);
+                mbar_wait_warp_spin(bar_aempty + 8 * slot, (use & 1) ^ 1);
                 const uint32_t base = sbase + NT_SA + slot * 16384;
                 const __half* src = kc < 4 ? a.A + kc * 64 : a.A2;
                 const long long ld = kc < 4 ? 256 : 64;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
             }
         }
     } else if (warp == kMmaWarp) {
-        mbar_wait(bar_b, 0);
+        mbar_wait_warp_spin(bar_b, 0);
         fence_async_smem();
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc_f16(256, 0, 0);
@@ -135,12 +137,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
         uint32_t it = 0, ch = 0;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t buf = it & 1, use = it >> 1;
-            mbar_wait(bar_accempty + 8 * buf, (use & 1) ^ 1);
+            mbar_wait_warp_spin(bar_accempty + 8 * buf, (use & 1) ^ 1);
             tc_fence_after();
             const uint32_t d = tmem_base + buf * 256u;
             for (int kc = 0; kc < n_chunks; ++kc, ++ch) {
                 const uint32_t slot = ch % NT_RING, cuse = ch / NT_RING;
-                mbar_wait(bar_afull + 8 * slot, cuse & 1);
+                mbar_wait_warp_spin(bar_afull + 8 * slot, cuse & 1);
                 fence_async_smem();          // the chunk was written by cp.async (generic proxy): order it before the MMA's reads
                 tc_fence_after();
 #pragma unroll
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            mbar_wait(bar_accfull + 8 * buf, use & 1);
+            mbar_wait_warp_spin(bar_accfull + 8 * buf, use & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
 #pragma unroll 1
@@ -262,7 +264,9 @@ constexpr uint32_t TN_SMEM = TN_BAR + 128;
 __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_constant__ TnArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index by lane-0 broadcast: descriptor / barrier arithmetic of the issuer then stays in uniform registers (see
+    // siren_fast3.cu); every wait below is therefore the vote-terminated form, which leaves the warp converged
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t bar_full = sbase + TN_BAR /* [3] */, bar_empty = bar_full + 24 /* [3] */, bar_done = bar_full + 48;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TN_BAR + 64);
     if (threadIdx.x == 0) {
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
     if (warp == kLoadWarp) {
         for (long long i = 0; i < n_mine; ++i) {
             const uint32_t st = (uint32_t)(i % TN_STAGES), use = (uint32_t)(i / TN_STAGES);
-            mbar_wait(bar_empty + 8 * st, (use & 1) ^ 1);
+            mbar_wait_warp_spin(bar_empty + 8 * st, (use & 1) ^ 1);
             const long long p0 = (slice + i * a.slices) * 64;
             const uint32_t sx = sbase + st * TN_STAGE_BYTES, sy = sx + 32768;
             // row k of the stage = point p0 + k: four 128-byte segments (64 features each) -> [k/8][seg][k%8][64]
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
         const uint64_t hi = desc_hi_mn(1024, 4096);
         for (long long i = 0; i < n_mine; ++i) {
             const uint32_t st = (uint32_t)(i % TN_STAGES), use = (uint32_t)(i / TN_STAGES);
-            mbar_wait(bar_full + 8 * st, use & 1);
+            mbar_wait_warp_spin(bar_full + 8 * st, use & 1);
             fence_async_smem();
             tc_fence_after();
             const uint32_t x_lo = (sbase + st * TN_STAGE_BYTES) >> 4, y_lo = x_lo + (32768 >> 4);
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
             float s0 = 0.f, s1 = 0.f;
             for (long long i = 0; i < n_mine; ++i) {
                 const uint32_t st = (uint32_t)(i % TN_STAGES), use = (uint32_t)(i / TN_STAGES);
-                mbar_wait(bar_full + 8 * st, use & 1);
+                mbar_wait_warp_spin(bar_full + 8 * st, use & 1);
                 const unsigned char* sx = smem + st * TN_STAGE_BYTES + (f >> 6) * 1024 + (f & 7) * 2;
 #pragma unroll 8
                 for (int k = 0; k < 64; ++k) {
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
             float* cs = a.colsum + ((size_t)b * a.slices + slice) * 256;
             cs[f] = s0; cs[f + 1] = s1;
         }
-        mbar_wait(bar_done, 0);
+        mbar_wait_warp_spin(bar_done, 0);
         tc_fence_after();
         float* out = a.partial + ((size_t)b * a.slices + slice) * 65536;
 #pragma unroll 1
