@@ -108,6 +108,29 @@ def test_field_fast_stage(runs, name):
     assert err.max() <= 3e-3, "max|fast field - oracle| = %g (per channel %s)" % (err.max(), err.amax((0, 1, 2)))
 
 
+@pytest.mark.parametrize("model", ["a_small", "b_small"])
+@pytest.mark.parametrize("n_points", [1, 127, 128, 129, 256, 389, 148 * 256 + 128, 148 * 512 + 37])
+def test_field_fast_tile_counts_against_the_fp32_path(model, n_points):
+    """One tile, a lone odd tile, a ragged last tile, one / two tile pairs per CTA plus a remainder: the persistent tcgen05
+    kernel against the fp32 path of the same library on the same points.  (Round 2 found that results depended on how
+    the issuer warps' lanes left their barrier waits once the issue instructions became warp-level: a single tile was
+    enough to show it.)"""
+    case = _cases.CASE_BY_NAME[model]
+    gen = _cases.build_mirror(case, DEV)
+    g = torch.Generator(device=DEV).manual_seed(n_points)
+    pts = (torch.rand(2, n_points, 3, device=DEV, generator=g) - 0.5) * 0.3
+    dirs = torch.nn.functional.normalize(torch.randn(2, n_points, 3, device=DEV, generator=g), dim=-1)
+    zs = [torch.randn(2, 256, device=DEV, generator=g) for _ in range(_cases.n_latents(model[0].upper()))]
+    with torch.no_grad():
+        film = gen.siren.film_from_latents(*zs)
+        fast = ops.siren_points(gen.siren, pts, film, dirs, precision="fast")
+        again = ops.siren_points(gen.siren, pts, film, dirs, precision="fast")
+        exact = ops.siren_points(gen.siren, pts, film, dirs, precision="exact")
+    assert torch.equal(fast, again), "two launches on the same inputs differ"
+    err = (fast - exact).abs().amax((0, 1))
+    assert torch.isfinite(fast).all() and err.max() <= 5e-3, "max|fast - exact| per channel %s" % err
+
+
 def _oracle_cdf(st, s):
     """The CDF sample_pdf searches (volumetric_rendering.py:273-277), from the oracle's coarse weights with the
     same torch ops on the same host, i.e. bit-identical to what the oracle's searchsorted saw."""
