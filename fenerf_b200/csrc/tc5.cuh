@@ -18,10 +18,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-// try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware until the phase flips
-// instead of spinning through issue slots the epilogue warps on the same scheduler need; the clock
-// watchdog only runs on the (rare) path where a suspended wait timed out.
+// Bounded waits: a protocol bug must surface as a launch failure, never as a hung GPU.
+// mbar_wait: per-thread, try_wait with a suspend-time hint (the waiting thread sleeps in hardware until the phase flips); used
+// by the single-lane ring producers.  mbar_wait_warp_spin: whole warp, no hint, converged exit; used by everything that goes
+// on to issue warp-level tcgen05 instructions.
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -35,16 +35,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
-// Whole-warp wait that ends CONVERGED: the loop exit is a warp vote, so every lane leaves in the same iteration.  Required in
-// front of warp-level tcgen05 issue (UTCHMMA / UTCBAR): lanes leaving a per-thread try_wait loop one by one re-issue them.
+// Whole-warp wait that ends CONVERGED (polls without the suspend-time hint): the loop exit is a warp vote, so every lane
+// leaves in the same iteration.  Required in front of warp-level tcgen05 issue (UTCHMMA / UTCBAR): lanes leaving a
+// per-thread try_wait loop one by one re-issue them.
 // (A trailing __syncwarp() is not enough: the compiler drops it where it believes the warp converged.)
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-    if (__all_sync(0xffffffffu, mbar_try(bar, parity))) return;
-    const long long t0 = clock64();
-    while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
 __device__ __forceinline__ void mbar_wait_warp_spin(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     for (;;) {
@@ -54,16 +48,6 @@ __device__ __forceinline__ void mbar_wait_warp_spin(uint32_t bar, uint32_t parit
         if (__all_sync(0xffffffffu, done)) return;
         if (clock64() - t0 > 4000000000LL) __trap();
     }
-}
-// Latency-critical single waiters (ring producers, MMA issuers): poll without the suspend-time hint.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    const long long t0 = clock64();
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && clock64() - t0 > 4000000000LL) __trap();
-    } while (!done);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
