@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         const uint32_t ring_lo = (sbase + SMEM_RING) >> 4;
         constexpr uint32_t kSlot16 = STAGE_BYTES >> 4, kChunk16 = CHUNK_BYTES >> 4;
         // one ring slot's "full" wait for a single-load step (slot number is a runtime value here)
-        // Every wait of the issuer ends with a warp vote (mbar_wait_warp): with the operand math in uniform registers ptxas
+        // Every wait of the issuer ends with a warp vote (mbar_wait_warp_spin): with the operand math in uniform registers ptxas
         // emits tcgen05.mma / commit as warp-level UTCHMMA / UTCBAR without the elect.sync, and lanes that left a per-thread
         // try_wait loop one by one issued them once per warp fragment (seen: K-steps accumulated twice).
         auto ctrl_wait = [&](uint32_t bar, uint32_t parity) { FN_CTRL_WAIT(bar, parity); };
