@@ -73,10 +73,9 @@ constexpr uint32_t SMEM_TOTAL = SMEM_TAB + MAX_LOADS * 16 + MAX_STAGES * 8;   //
 // The MMA issuers poll their barriers without the suspend-time hint, and every wait ends in a warp vote
 // (tc5.cuh: mbar_wait_warp_spin).  Measured (tools/ablate_fast3.sh): 2 % faster than the sleeping try_wait -- and with six
 // 16 KB ring slots the hinted try_wait on the ring's transaction barriers produced wrong results from a single tile on
-// (cause not identified; the hinted form stays in use only on the epilogue / producer side, where every configuration
-// passes the parity tests).
+// (cause not identified; no wait of this kernel uses the hinted form any more).
 #define FN_CTRL_WAIT mbar_wait_warp_spin
-#define FN_PROD_WAIT mbar_wait                  // (polling here measured no different)
+#define FN_PROD_WAIT mbar_wait_poll             // (single lane; measured no different from the hinted form, kept uniform with the rest)
 #define FN_EPI_WAIT mbar_wait_warp_spin     // epilogue warps wait converged as well (tcgen05.ld is .sync.aligned); +0.5-1 % over the hinted form
 #ifdef FENERF_AB_LD32
 constexpr int GW = 32;                               // TMEM columns per tcgen05.ld in the FiLM epilogue

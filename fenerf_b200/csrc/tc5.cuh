@@ -19,9 +19,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
                  : "memory");
 }
 // Bounded waits: a protocol bug must surface as a launch failure, never as a hung GPU.
-// mbar_wait: per-thread, try_wait with a suspend-time hint (the waiting thread sleeps in hardware until the phase flips); used
-// by the single-lane ring producers.  mbar_wait_warp_spin: whole warp, no hint, converged exit; used by everything that goes
-// on to issue warp-level tcgen05 instructions.
+// mbar_wait: per-thread, try_wait with a suspend-time hint (the waiting thread sleeps in hardware until the phase flips); no
+// longer used by the tcgen05 kernels (see siren_fast3.cu).  mbar_wait_poll: per-thread, no hint (single-lane producers).
+// mbar_wait_warp_spin: whole warp, no hint, converged exit; used by everything that goes on to issue warp-level tcgen05
+// instructions.
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -46,6 +47,17 @@ __device__ __forceinline__ void mbar_wait_warp_spin(uint32_t bar, uint32_t parit
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (__all_sync(0xffffffffu, done)) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+// Per-thread poll without the hint (single-lane roles: the ring producers).
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
