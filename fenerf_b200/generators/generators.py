@@ -115,10 +115,23 @@ class _RenderSkeleton:
             depth = wsum = weights = None
         return pixels, depth, wsum, weights, pitch, yaw
 
-    def _check_no_neural_renderer(self):
-        if getattr(self, 'neural_renderer_img', None) or getattr(self, 'neural_renderer_seg', None):
-            raise NotImplementedError("neural_renderer_img/seg upsamplers are outside the B200 hot path "
-                                      "(SURVEY.md section 2 row 12)")
+    def _finish_pixels(self, pixels):
+        """The tail every reference method ends in (generators.py:102-118, 231-248, 333-350, 414-430): without
+        upsamplers the frame is ``permute(0,3,1,2) * 2 - 1`` -- what the compositing kernel already wrote; with
+        ``neural_renderer_img`` (and ``neural_renderer_seg``: the first 64 channels are label features, the rest
+        image features) the caller's modules run on the [0, 1] frame and the ``* 2 - 1`` follows them.  The modules
+        are the caller's own ``nn.Module``s (generators/neural_rendering.py) and stay PyTorch; autograd reaches the
+        render through the affine below."""
+        img, seg = getattr(self, 'neural_renderer_img', None), getattr(self, 'neural_renderer_seg', None)
+        if not img and not seg:
+            return pixels
+        unit = (pixels + 1) * 0.5          # undo the kernel's * 2 - 1 (exact to one rounding of a value in [-1, 1])
+        if seg:
+            labels, images = unit[:, :64], unit[:, 64:]
+            images = img(images)
+            labels = seg(labels)
+            return torch.cat([labels, images], dim=1) * 2 - 1
+        return img(unit) * 2 - 1
 
     def _third_output(self, pixels, wsum, weights, batch_size, img_size):
         """The reference's third return of staged_*: per-sample weights for fill modes that return
@@ -165,18 +178,16 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
                 hierarchical_sample, sample_dist=None, lock_view_dependence=False, **kwargs):
         if 'img_feat_size' in kwargs:
             img_size = kwargs['img_feat_size']
-        self._check_no_neural_renderer()
         pixels, _, _, _, pitch, yaw = self._render(
             self.siren.film_from_latents(z), z.shape[0], img_size, fov, ray_start, ray_end, num_steps, h_stddev,
             v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs, staged=False)
-        return pixels, torch.cat([pitch, yaw], -1)
+        return self._finish_pixels(pixels), torch.cat([pitch, yaw], -1)
 
     def staged_forward(self, z, img_size, fov, ray_start, ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean,
                        psi=1, lock_view_dependence=False, max_batch_size=50000, depth_map=False, near_clip=0,
                        far_clip=2, sample_dist=None, hierarchical_sample=False, **kwargs):
         if 'img_feat_size' in kwargs:
             img_size = kwargs['img_feat_size']
-        self._check_no_neural_renderer()
         batch_size = z.shape[0]
         self.generate_avg_frequencies(rng=kwargs.get('_avg_rng'))
         with torch.no_grad():
@@ -189,7 +200,7 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
             # the reference reshapes its third output to channel_dim channels (generators.py:224):
             # only the weights_sum-returning fill modes fit that; weights_sum is returned for all
             third = self._third_output(pixels, wsum, None, batch_size, img_size)
-        return pixels, depth_map, third
+        return self._finish_pixels(pixels), depth_map, third
 
     def staged_forward_with_frequencies(self, truncated_frequencies, truncated_phase_shifts, img_size, fov, ray_start,
                                         ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean, psi=0.7,
@@ -197,7 +208,6 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
                                         near_clip=0, far_clip=2, sample_dist=None, hierarchical_sample=False, **kwargs):
         if 'img_feat_size' in kwargs:
             img_size = kwargs['img_feat_size']
-        self._check_no_neural_renderer()
         batch_size = truncated_frequencies.shape[0]
         with torch.no_grad():
             pixels, depth, _, _, _, _ = self._render(
@@ -205,19 +215,18 @@ class ImplicitGenerator3d(_RenderSkeleton, nn.Module):
                 ray_end, num_steps, h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist,
                 lock_view_dependence, kwargs, staged=True)
             depth_map = depth.reshape(batch_size, img_size, img_size).contiguous().cpu()
-        return pixels, depth_map
+        return self._finish_pixels(pixels), depth_map
 
     def forward_with_frequencies(self, frequencies, phase_shifts, img_size, fov, ray_start, ray_end, num_steps,
                                  h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist=None,
                                  lock_view_dependence=False, **kwargs):
         if 'img_feat_size' in kwargs:
             img_size = kwargs['img_feat_size']
-        self._check_no_neural_renderer()
         pixels, _, _, _, pitch, yaw = self._render(
             self._film(frequencies, phase_shifts), frequencies.shape[0], img_size, fov, ray_start, ray_end, num_steps,
             h_stddev, v_stddev, h_mean, v_mean, hierarchical_sample, sample_dist, lock_view_dependence, kwargs,
             staged=False)
-        return pixels, torch.cat([pitch, yaw], -1)
+        return self._finish_pixels(pixels), torch.cat([pitch, yaw], -1)
 
 
 class StyleGenerator3d(ImplicitGenerator3d):
@@ -235,7 +244,6 @@ class StyleGenerator3d(ImplicitGenerator3d):
                        far_clip=2, sample_dist=None, hierarchical_sample=False, **kwargs):
         if 'img_feat_size' in kwargs:
             img_size = kwargs['img_feat_size']
-        self._check_no_neural_renderer()
         batch_size = z.shape[0]
         with torch.no_grad():
             pixels, depth, wsum, _, _, _ = self._render(
@@ -244,7 +252,7 @@ class StyleGenerator3d(ImplicitGenerator3d):
                 staged=True)
             depth_map = depth.reshape(batch_size, img_size, img_size).contiguous().cpu()
             third = self._third_output(pixels, wsum, None, batch_size, img_size)
-        return pixels, depth_map, third
+        return self._finish_pixels(pixels), depth_map, third
 
 
 class DoubleImplicitGenerator3d(_RenderSkeleton, nn.Module):

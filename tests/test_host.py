@@ -169,3 +169,36 @@ def test_frame_gather_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_neural_renderer_tail_matches_the_reference_tail():
+    """generators.py:102-118 (and the three staged copies): with upsampler modules attached the [0, 1] frame goes
+    through them and `* 2 - 1` follows; the kernels write `* 2 - 1` frames, `_finish_pixels` undoes and redoes it."""
+    import types
+    import torch.nn as nn
+    from fenerf_b200.generators.generators import _RenderSkeleton
+    torch.manual_seed(3)
+    unit = torch.rand(2, 8, 8, 67)                                # what fancy_integration returns, reshaped (B,R,R,C-1)
+    kernel_frame = unit.permute(0, 3, 1, 2).contiguous() * 2 - 1   # what the compositing kernel writes
+    img = nn.Sequential(nn.Upsample(scale_factor=2.), nn.Conv2d(3, 3, 3, 1, 1), nn.Sigmoid())
+    seg = nn.Sequential(nn.Upsample(scale_factor=2.), nn.Conv2d(64, 19, 3, 1, 1))
+    none = types.SimpleNamespace(neural_renderer_img=None, neural_renderer_seg=None)
+    assert _RenderSkeleton._finish_pixels(none, kernel_frame) is kernel_frame
+    with torch.no_grad():
+        # reference tail, image renderer only (fed the whole frame there: use a 67 -> 3 module)
+        img67 = nn.Sequential(nn.Conv2d(67, 3, 1), nn.Sigmoid())
+        want = img67(unit.permute(0, 3, 1, 2).contiguous()) * 2 - 1
+        got = _RenderSkeleton._finish_pixels(types.SimpleNamespace(neural_renderer_img=img67, neural_renderer_seg=None),
+                                             kernel_frame)
+        assert got.shape == want.shape and (got - want).abs().max() < 1e-6
+        # reference tail with both: first 64 channels -> seg renderer, rest -> image renderer, labels first
+        p = unit.permute(0, 3, 1, 2).contiguous()
+        want = torch.cat([seg(p[:, :64]), img(p[:, 64:])], dim=1) * 2 - 1
+        got = _RenderSkeleton._finish_pixels(types.SimpleNamespace(neural_renderer_img=img, neural_renderer_seg=seg),
+                                             kernel_frame)
+        assert got.shape == (2, 22, 16, 16) and (got - want).abs().max() < 1e-5
+    # autograd reaches the frame through the tail (the G step differentiates through the upsamplers)
+    frame = kernel_frame.clone().requires_grad_(True)
+    _RenderSkeleton._finish_pixels(types.SimpleNamespace(neural_renderer_img=img67, neural_renderer_seg=None),
+                                   frame).sum().backward()
+    assert frame.grad is not None and frame.grad.abs().sum() > 0
