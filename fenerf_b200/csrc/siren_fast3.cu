@@ -83,6 +83,20 @@ constexpr uint32_t SMEM_TOTAL = SMEM_TAB + MAX_LOADS * 16 + MAX_STAGES * 8;   //
 #define FENERF_AB_SEQ_LAG 2
 #endif
 constexpr uint32_t SEQ_LAG = FENERF_AB_SEQ_LAG;
+// Shared ring (experiment switch).  Every ring load is weight data, the same for both tiles of a pair: with SHARE_RING each slab is
+// loaded ONCE per pair and read by both issuers (one `full` barrier per slot that both wait on, `empty` counts two commits), which
+// halves the L2 -> shared-memory weight stream and doubles the time a slot may take to turn around.  The two tiles then run at
+// most RING rounds apart (the leader waits for the follower to release the slot).  With a single tile in the pair the idle issuer
+// releases the slots without issuing MMAs.
+#ifndef FENERF_AB_SHARE
+#define FENERF_AB_SHARE 0
+#endif
+constexpr bool SHARE_RING = FENERF_AB_SHARE != 0;
+// The flat (per-load) ring orders above are compiled in only with -DFENERF_AB_FLAT=1; the default build keeps the stage-by-stage
+// order  X s, Y s, X s+1, ...  that every committed measurement was taken with.
+#ifndef FENERF_AB_FLAT
+#define FENERF_AB_FLAT (FENERF_AB_SHARE != 0)
+#endif
 #define FN_PROD_WAIT mbar_wait_poll             // (single lane; measured no different from the hinted form, kept uniform with the rest)
 #define FN_EPI_WAIT mbar_wait_warp_spin     // epilogue warps wait converged as well (tcgen05.ld is .sync.aligned); +0.5-1 % over the hinted form
 #ifdef FENERF_AB_LD32
@@ -178,7 +192,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
     for (int i = threadIdx.x; i < a.n_stages; i += NTHREADS) s_stages[i] = a.stages[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING; ++i) {
+#if FENERF_AB_FLAT
+            mbar_init(bar_full + 16 * i, 1); mbar_init(bar_full + 16 * i + 8, 1); mbar_init(bar_empty + 8 * i, SHARE_RING ? 2 : 1);
+#else
             mbar_init(bar_full + 16 * i, 1); mbar_init(bar_full + 16 * i + 8, 1); mbar_init(bar_empty + 8 * i, 1);
+#endif
         }
         for (int t = 0; t < 2; ++t) {
             for (int h = 0; h < 2; ++h) {
@@ -207,6 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         // first load of a phase was requested two rounds before the previous phase ended.)
         if (lane == 0) {
             uint32_t it = 0, empty_par = 0;         // bit s: parity of the next wait on empty[s] (starts "free")
+#if FENERF_AB_FLAT
             const uint32_t n_flat = (uint32_t)a.n_loads;
             auto emit = [&](int t, uint32_t li) {
                 if ((int)(it % PROD) == warp) {
@@ -222,12 +241,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                 }
                 ++it;
             };
+#endif
             for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x) {
                 const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
-                const uint32_t n_iter = n_flat + (nt == 2 ? SEQ_LAG : 0u);
+#if FENERF_AB_FLAT
+                const uint32_t n_iter = n_flat + ((nt == 2 && !SHARE_RING) ? SEQ_LAG : 0u);
+                if (SHARE_RING) {
+                    for (uint32_t i = 0; i < n_flat; ++i) emit(0, i);
+                } else
                 for (uint32_t i = 0; i < n_iter; ++i) {
                     if (i < n_flat) emit(0, i);
                     if (nt == 2 && i >= SEQ_LAG && i - SEQ_LAG < n_flat) emit(1, i - SEQ_LAG);
+#else
+                for (int s = 0; s < a.n_stages;) {
+                    int s_end = s + 1;
+                    while (s_stages[s_end - 1].fuse_next) ++s_end;
+                    for (int t = 0; t < nt; ++t)
+                        for (int ss = s; ss < s_end; ++ss) {
+                            const int n = s_stages[ss].n_loads, li = s_stages[ss].l0;
+                            for (int j = 0; j < n; ++j, ++it) {
+                                if ((int)(it % PROD) != warp) continue;
+                                const uint32_t slot = it % RING;
+                                const LoadOp op = s_loads[li + j];          // before the wait: off the turnaround path
+                                uint32_t bytes = (uint32_t)op.bytes16 * 16u;
+                                if (FN_DBG(1)) bytes = 1024u;               // timing experiment only: wrong results
+                                const unsigned char* src = a.packed + op.src;
+                                FN_PROD_WAIT(bar_empty + 8 * slot, ((empty_par >> slot) & 1u) ^ 1u);
+                                empty_par ^= 1u << slot;
+                                mbar_arrive_expect_tx(bar_full + 16 * slot + 8 * t, bytes);
+                                bulk_g2s(sbase + SMEM_RING + slot * STAGE_BYTES, src, bytes, bar_full + 16 * slot + 8 * t);
+                            }
+                        }
+                    s = s_end;
+#endif
                 }
             }
         }
@@ -238,6 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         // other issuer's MMAs instead of idling the tensor pipe.
         const int t = warp - MMA_WARP;
         uint32_t full_par = 0;                      // bit s: phase parity of full[s][t] this tile waits for next
+#if FENERF_AB_FLAT
         uint32_t it = 0;                            // flat load index of this tile's program within the current pair
         uint32_t seq_base = 0;                      // ring position of the pair's first entry
         int nt_cur = 2;
@@ -245,11 +292,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         // ring slot of this tile's load `it` (the producers' emission order, see SEQ_LAG)
         auto slot_now = [&]() -> uint32_t {
             uint32_t pos;
-            if (nt_cur == 1) pos = it;
+            if (SHARE_RING || nt_cur == 1) pos = it;
             else if (t == 0) pos = it < SEQ_LAG ? it : 2u * it - SEQ_LAG;
             else pos = (it + SEQ_LAG + 1u < n_flat ? it + SEQ_LAG + 1u : n_flat) + it;
             return (seq_base + pos) % RING;
         };
+#else
+        uint32_t it = 0;                            // global load number (slot = it % RING), as in the producers
+#endif
         uint32_t n_ready = 0, n_x = 0;
         Tracer<kTrace> tr(lane == 0 ? a.trace : nullptr, t == 0 ? 1 : 0);
         const uint32_t ring_lo = (sbase + SMEM_RING) >> 4;
@@ -260,7 +310,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         // try_wait loop one by one issued them once per warp fragment (seen: K-steps accumulated twice).
         auto ctrl_wait = [&](uint32_t bar, uint32_t parity) { FN_CTRL_WAIT(bar, parity); };
         auto wait_full = [&](uint32_t slot) {
+#if FENERF_AB_FLAT
+            ctrl_wait(bar_full + 16 * slot + (SHARE_RING ? 0 : 8 * t), (full_par >> slot) & 1u);
+#else
             ctrl_wait(bar_full + 16 * slot + 8 * t, (full_par >> slot) & 1u);
+#endif
             tc_fence_after();
             full_par ^= 1u << slot;
         };
@@ -274,12 +328,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
         int tl = 0;
         for (long long pair = blockIdx.x; pair * 2 < a.n_tiles; pair += gridDim.x, ++tl) {
             const int nt = (pair * 2 + 1 < a.n_tiles) ? 2 : 1;
+#if FENERF_AB_FLAT
             nt_cur = nt;
             it = 0;
             if (t < nt) {
                 {
                     for (int ss = 0; ss < a.n_stages; ++ss) {
+#else
+            for (int s = 0; s < a.n_stages;) {
+                int s_end = s + 1;
+                while ((m_fuse >> (s_end - 1)) & 1u) ++s_end;
+                for (int tt = 0; tt < nt; ++tt) {
+                    for (int ss = s; ss < s_end; ++ss) {
+#endif
                         const bool st_uniform = (m_uniform >> ss) & 1u, st_xsync = (m_xsync >> ss) & 1u;
+#if FENERF_AB_FLAT
+#else
+                        if (tt != t) {                       // the other issuer's phase: only the ring position moves
+                            it += s_stages[ss].n_loads;
+                            continue;
+                        }
+#endif
                         tr.log('B', tl, ss, t);
                         const uint32_t rdy_par = n_ready & 1;
                         ++n_ready;
@@ -293,7 +362,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         // K-major input slots (positions in chunk 3 / direction + grid features in chunk 0) against
                         // the [256 features][64 slots] weight image: one MMA group per feature half
                         auto x_load = [&](const LoadOp op) {
+#if FENERF_AB_FLAT
                             const uint32_t slot = slot_now();
+#else
+                            const uint32_t slot = it % RING;
+#endif
                             wait_full(slot);
                             tr.log('F', tl, ss, t * 64 + 4);
                             const uint32_t x_lo = x_lo0 + (op.xkind == X_POS ? 3u : 0u) * kChunk16;
@@ -322,7 +395,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             for (int r = 0; r < 8 / SLAB_CHUNKS; ++r) {
                                 // the first h1 piece needs accumulator half 1 drained (and, later, chunks 2,3)
                                 if (r * SLAB_CHUNKS == 2) ctrl_wait(bar_aready + 8 * (t * 2 + 1), rdy_par);
+#if FENERF_AB_FLAT
                                 const uint32_t slot = slot_now();
+#else
+                                const uint32_t slot = it % RING;
+#endif
                                 wait_full(slot);
                                 tr.log('F', tl, ss, t * 64 + r);
 #pragma unroll
@@ -365,7 +442,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                             // head: activations are the A operand (M = 128 points, MN-major), the [n rows][256] head
                             // image the B operand; 4 k-chunks x 4 K-steps, fully unrolled
                             const LoadOp op = s_loads[s_stages[ss].l0];
+#if FENERF_AB_FLAT
                             const uint32_t slot = slot_now();
+#else
+                            const uint32_t slot = it % RING;
+#endif
                             wait_full(slot);
                             tr.log('F', tl, ss, t * 64);
                             const uint32_t idesc = umma_idesc_f16((uint32_t)op.n8 * 8u, 1u, 0u);
@@ -385,8 +466,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) siren_fast3_kernel(const __grid_c
                         tr.log('C', tl, ss, t);
                     }
                 }
+#if FENERF_AB_FLAT
+#else
+                s = s_end;
+#endif
             }
-            seq_base += nt == 2 ? 2u * n_flat : n_flat;
+#if FENERF_AB_FLAT
+            else if (SHARE_RING) {
+                // single tile in this pair: the idle issuer still releases every slot (empty counts two arrivals)
+                for (uint32_t i = 0; i < n_flat; ++i, ++it) {
+                    const uint32_t slot = slot_now();
+                    wait_full(slot);
+                    if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+                    __syncwarp();
+                }
+            }
+            seq_base += (nt == 2 && !SHARE_RING) ? 2u * n_flat : n_flat;
+#endif
         }
     } else {
         // ================= epilogue warps =================
