@@ -692,3 +692,40 @@ def test_repack_after_inplace_weight_update():
         gen.siren.final_layer.bias += 0.5      # what an optimizer step / EMA copy_to does
         torch.manual_seed(5); b, _ = gen(z, **case.cfg)
     assert (a - b).abs().max() > 1e-3, "packed weights were not refreshed after an in-place update"
+
+
+def test_neural_renderer_modules_run_on_the_unit_frame(runs):
+    """generators.py:102-118, 231-248: with `neural_renderer_img` attached the caller's module runs on the [0, 1]
+    frame and `* 2 - 1` follows; checked against the same module applied to the reference's golden frame, for
+    `forward`, `staged_forward`, and with autograd through the module into the field's weights."""
+    torch.manual_seed(9)
+    up = torch.nn.Sequential(torch.nn.Upsample(scale_factor=2.), torch.nn.Conv2d(3, 3, 3, 1, 1), torch.nn.Sigmoid()).to(DEV)
+    for name in ("a_small", "a_staged_white"):
+        case, run = runs(name)
+        gold = torch.from_numpy(np.load(_cases.golden_path(case))["pixels"])
+        with torch.no_grad():
+            want = (up(((gold + 1) * 0.5).to(DEV)) * 2 - 1).cpu()
+        gen = _cases.build_mirror(case, DEV)
+        gen.neural_renderer_img = up
+        kw = dict(case.cfg, precision="guard", _rng=ReplayRng(run["draws"], DEV))
+        with torch.no_grad():
+            if case.method == "staged_forward":
+                avg = ReplayRng([("randn", t) for t in run["avg_draws"]], DEV)
+                got = gen.staged_forward(*[_cuda(z) for z in run["latents"]], psi=case.psi, _avg_rng=avg, **kw)[0].cpu()
+            else:
+                got = gen(*[_cuda(z) for z in run["latents"]], **kw)[0].cpu()
+        r = case.cfg["img_size"]
+        assert got.shape == (case.batch, 3, 2 * r, 2 * r)
+        # a 3x3 convolution spreads an ill-conditioned ray over its neighbours: bound the bulk, not every pixel
+        err = (got - want).abs()
+        assert err.median() <= 1e-4 and (err > 1e-3).float().mean() <= 0.02
+    case, run = runs("a_small")
+    gen = _cases.build_mirror(case, DEV)
+    gen.neural_renderer_img = up
+    kw = dict(case.cfg, _rng=ReplayRng(run["draws"], DEV))
+    frames, _ = gen(*[_cuda(z) for z in run["latents"]], **kw)
+    assert frames.requires_grad
+    frames.square().mean().backward()
+    g = gen.siren.final_layer.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+    assert up[1].weight.grad is not None and up[1].weight.grad.abs().sum() > 0
