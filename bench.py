@@ -31,6 +31,7 @@ import torch  # noqa: E402
 FLOP_PER_POINT = {"A": 1053696, "B": 1341440}   # SURVEY.md section 8d (B: label chain pre-multiplied)
 MODEL_NAME = {"A": "ImplicitGenerator3d+TALLSIREN", "B": "DoubleImplicitGenerator3d+TextureEmbeddingPiGAN256SEMANTICDISENTANGLE_DIM_96"}
 IMG, STEPS_PER_RAY, BATCH_PER_GPU = 128, 24, 4
+SETTLE_S = 1.0      # idle time in front of every timed arm (StepRunner.settle)
 
 
 def metadata(img_size=IMG):
@@ -280,8 +281,17 @@ class StepRunner:
         self.out_done[i & 1].synchronize()
         self.host_sink += float(self.out_host[i & 1][0, 0, 0, 0]) + float(self.out_host[i & 1][-1, -1, -1, -1])
 
+    def settle(self):
+        """Both arms start from the same device state: queue drained, then SETTLE_S of idle, then their warm-up steps.  On
+        this part the power limiter pulls the SM clock down within ~0.1-0.2 s of full load (profiles/r02_diag_e2e.txt:
+        the same graph replay takes 3.13-3.18 ms per step in a 20-step burst from idle and 3.48-3.56 ms once capped, with or
+        without the host copies), so an arm timed right behind another one measured the limiter, not its pipeline."""
+        torch.cuda.synchronize()
+        time.sleep(SETTLE_S)
+
     def time_resident(self, steps, warmup):
         from fenerf_b200 import _lib
+        self.settle()
         for i in range(warmup):
             self.step_resident(i)
         barrier(self.world); torch.cuda.synchronize()
@@ -296,8 +306,9 @@ class StepRunner:
         return ms, _lib.launch_count() - l0
 
     def time_e2e(self, steps, warmup):
-        n_pre = min(warmup, 2)
+        n_pre = warmup
         self.first_e2e = 0
+        self.settle()
         for i in range(n_pre):
             self.step_e2e(i)
         if n_pre:
