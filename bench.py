@@ -8,7 +8,9 @@ A "step" is one pass of the hot path over one batch of synthetic latents: BASELI
 -- 128x128 image, 24 (+24 hierarchical) samples per ray, batch 4 per GPU, forward-only -- through
 the reference-facing generator API (``generator(z, **metadata)`` under no_grad), then the frame
 all-gather when N > 1.  Weights are the reference's random init under manual_seed(0); latents are
-N(0,1); camera poses gaussian (h_stddev 0.3, v_stddev 0.155); nerf_noise 0.  One JSON line on
+N(0,1); camera poses gaussian (h_stddev 0.3, v_stddev 0.155); nerf_noise 0.  Every timed arm (resident,
+end to end, per model and precision mode) starts from the same device state: queue drained, SETTLE_S
+of idle, W warm-up steps, then exactly K timed steps (StepRunner.settle says why).  One JSON line on
 stdout (rank 0).  Nothing here reads /root/reference.
 """
 import argparse
